@@ -1,0 +1,102 @@
+/* nm_b200.h -- status-returning C ABI of libnm_b200.so (B200 / sm_100a implementation of the
+ * NormalModes hot path: distributed CSR SpMV, ChebIter, Chebyshev-filtered Lanczos, FE assembly).
+ * Plain pointers and sizes only.  Every function returns 0 on success, non-zero on error with the
+ * message available from nm_last_error_message().  Unless a name ends in _dev, vector arguments
+ * are HOST pointers and the call synchronises; _dev variants take DEVICE pointers and are
+ * asynchronous on nm_stream().
+ *
+ * Each group cites the reference interface it replaces (file:line into /root/reference/src).
+ * The by-reference Fortran twins the reference actually links are declared in pevsl_f90.h.
+ */
+#ifndef NM_B200_H
+#define NM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void (*nm_matvec_fn)(double* x, double* y, void* data);
+
+/* ---- errors ---------------------------------------------------------------------------------- */
+int nm_last_error(void);
+const char* nm_last_error_message(void);
+void nm_clear_error(void);
+
+/* ---- runtime: one process per GPU ------------------------------------------------------------- */
+int nm_init(int device);                                   /* device < 0: keep the current CUDA device */
+int nm_device_info(int* device, int* sm_count, int* rank, int* nranks);
+long long nm_launch_count(void);                           /* kernels launched by this library so far */
+void* nm_stream(void);                                     /* cudaStream_t all work is queued on */
+int nm_sync(void);
+/* NCCL communicator replacing mymatvec%comm (mod_matvec.f90:75): rank 0 creates the id, the host
+ * broadcasts the 128 bytes (MPI_Bcast / torch.distributed), every rank calls nm_comm_init. */
+int nm_comm_unique_id(char* id128);
+int nm_comm_init(int rank, int nranks, const char* id128);
+int nm_comm_finalize(void);
+
+/* ---- distributed CSR: pevsl_parcsrcreate_f90 / pevsl_parcsrmatvec_f90 (mod_matvec.f90:69,453) ---- */
+int nm_parcsr_create(int nrow_glob, int ncol_glob, const int* row_starts, const int* col_starts, const int* ia,
+                     const int* ja, const double* a, void** mat_out);
+int nm_parcsr_free(void* mat);
+int nm_parcsr_matvec(void* mat, const double* x, double* y);
+int nm_parcsr_matvec_dev(void* mat, const double* x_dev, double* y_dev);
+/* format: 0 CSR, 1 ROW3 (shared column triples), 2 KRON3 (M (x) I3); fmt_bytes: matrix bytes one SpMV streams */
+int nm_parcsr_info(void* mat, int* nrow, int* ncol, long long* nnz, int* format, int* nghost, long long* fmt_bytes);
+
+/* Bdiagscaling / Apdiagscaling (mod_matvec.f90:252-342,345-441) on the device, in place:
+ * d_i = 1/sqrt(sign*M_ii), M~_ij = (sign*M_ij*d_j)*d_i ; d_host[n_local] receives d (may be NULL). */
+int nm_parcsr_jacobi_scale(void* mat, double sign, double* d_host);
+int nm_parcsr_get_values(void* mat, double* a_host /* nnz_local */);
+
+/* ---- ChebIter: pevsl_setup_chebiter_f90 / pevsl_chebiter_f90 (mod_matvec.f90:93,174,480,512) ---- */
+int nm_chebiter_create(double lmin, double lmax, int deg, void* mat, void** cheb_out);
+int nm_chebiter_free(void* cheb);
+int nm_chebiter_solve_host(void* cheb, const double* b, double* x);
+int nm_chebiter_solve_dev(void* cheb, const double* b_dev, double* x_dev);
+int nm_chebiter_stats(void* cheb, long long* nsolve, long long* nmatvec, int* deg, double* lmin, double* lmax);
+
+/* ---- operators: the callbacks sparseAV / sparsefsAV / sparseBV / sparseApV (mod_matvec.f90:445-520) ---- */
+int nm_op_create_csr(void* mat, void** op_out);                               /* w = M v                        */
+int nm_op_create_solid(void* A, const double* d, void** op_out);              /* w = D A D v          (:445-458) */
+int nm_op_create_fluidsolid(void* Ad, void* E, void* ET, void* chebAp, const double* d, const double* dp,
+                            void** op_out);                                   /* w = D[Ad+E Dp Ap~^-1 Dp ET]D v (:498-520) */
+int nm_op_create_callback(int n_local, nm_matvec_fn fn, void* data, void** op_out);
+int nm_op_free(void* op);
+int nm_op_apply_host(void* op, const double* x, double* y);
+int nm_op_apply_dev(void* op, const double* x_dev, double* y_dev);
+
+/* ---- filter polynomial: pevsl_findpol_f90 / pevsl_freepol_f90 (mod_pevsl.f90:115,215); host only ---- */
+int nm_findpol_create(const double* xintv4, double thresh_int, double thresh_ext, void** pol_out);
+int nm_pol_info(void* pol, int* deg, double* cc, double* dd, double* gam, double* bar, int* type);
+int nm_pol_coeffs(void* pol, double* mu /* deg+1 */);
+int nm_pol_free(void* pol);
+int nm_tridiag_eig_host(int k, const double* d, const double* e, double* w, double* Z, double* lastrow);
+
+/* ---- solver context: pevsl_start .. pevsl_copy_result (mod_pevsl.f90:54-130) ---- */
+int nm_pevsl_create(void** pevsl_out);
+int nm_pevsl_free(void* pevsl);
+int nm_pevsl_setprobsizes(void* pevsl, int N_global, int n_local, int nfirst);
+int nm_pevsl_set_nfirst(void* pevsl, int nfirst);          /* first global row of this rank (start-vector keying) */
+int nm_pevsl_setamv_callback(void* pevsl, nm_matvec_fn fn, void* data);
+int nm_pevsl_setbmv_callback(void* pevsl, nm_matvec_fn fn, void* data);
+int nm_pevsl_setamv_op(void* pevsl, void* op);
+int nm_pevsl_setbmv_op(void* pevsl, void* op);
+int nm_pevsl_adopt_op(void* pevsl, void* op);
+int nm_pevsl_setbsol_chebiter(void* pevsl, void* cheb);
+int nm_pevsl_set_geneig(void* pevsl);
+int nm_pevsl_set_seed(void* pevsl, unsigned long long seed);
+int nm_pevsl_lanbounds(void* pevsl, int mlan, int lanstep, double tol, double* lmin, double* lmax);
+int nm_pevsl_cheblannr(void* pevsl, const double* xintv4, int maxit, double tol, void* pol);
+int nm_pevsl_get_nev(void* pevsl, int* nev);
+int nm_pevsl_copy_result(void* pevsl, double* vals, double* vecs, int ld, double* res /* may be NULL */);
+int nm_pevsl_stats(void* pevsl, int* steps, int* deg, double* t_total, double* t_filter, double* t_reorth,
+                   double* t_ritz, long long* n_filter);
+/* one application y = p(A B^-1) z of the polynomial filter (ChebAv), the unit of the headline metric */
+int nm_pevsl_filter_host(void* pevsl, void* pol, const double* z, double* y);
+int nm_pevsl_filter_dev(void* pevsl, void* pol, const double* z_dev, double* y_dev, double* work3n_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

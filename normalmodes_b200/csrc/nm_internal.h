@@ -1,0 +1,228 @@
+// normalmodes_b200 -- internal declarations shared by the CUDA translation units.
+// Nothing in here is part of the C ABI (see include/nm_b200.h, include/pevsl_f90.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <memory>
+
+#define NM_OK 0
+#define NM_ERR 1
+
+// ---------------------------------------------------------------- errors
+struct NmError : public std::runtime_error {
+  explicit NmError(const std::string& s) : std::runtime_error(s) {}
+};
+void nm_fail(const char* file, int line, const char* fmt, ...);
+void nm_record_error(const char* msg);
+#define NM_CUDA(x)                                                                         \
+  do {                                                                                     \
+    cudaError_t e_ = (x);                                                                  \
+    if (e_ != cudaSuccess) nm_fail(__FILE__, __LINE__, "CUDA: %s (%s)", cudaGetErrorString(e_), #x); \
+  } while (0)
+#define NM_NCCL(x)                                                                         \
+  do {                                                                                     \
+    ncclResult_t e_ = (x);                                                                 \
+    if (e_ != ncclSuccess) nm_fail(__FILE__, __LINE__, "NCCL: %s (%s)", ncclGetErrorString(e_), #x); \
+  } while (0)
+#define NM_REQUIRE(c, ...)                                  \
+  do {                                                      \
+    if (!(c)) nm_fail(__FILE__, __LINE__, __VA_ARGS__);     \
+  } while (0)
+// C-ABI wrappers: run body, convert exceptions into an error code + message.
+#define NM_API_BEGIN try {
+#define NM_API_END                               \
+  }                                              \
+  catch (const std::exception& e) {              \
+    nm_record_error(e.what());                   \
+    return NM_ERR;                               \
+  }                                              \
+  return NM_OK;
+
+// ---------------------------------------------------------------- runtime context
+struct NmCtx {
+  bool ready = false;
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  int rank = 0, nranks = 1;
+  ncclComm_t nccl = nullptr;
+  double* d_red = nullptr;        // reduction scratch (partials), device
+  size_t d_red_cap = 0;
+  double* h_pin = nullptr;        // small pinned host scratch
+  size_t h_pin_cap = 0;
+  long launches = 0;              // kernels launched by this library (bench 'gpu_launches')
+};
+NmCtx& nm_ctx();
+void nm_ensure_init();
+double* nm_red_scratch(size_t n);
+double* nm_pinned(size_t n);
+
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DBuf() {}
+  explicit DBuf(size_t n_) { alloc(n_); }
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  DBuf(DBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DBuf& operator=(DBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DBuf() { release(); }
+  void alloc(size_t n_) {
+    release();
+    n = n_;
+    if (n) NM_CUDA(cudaMalloc((void**)&p, n * sizeof(T)));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  void upload(const T* h, size_t cnt) {
+    if (cnt) NM_CUDA(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, nm_ctx().stream));
+    NM_CUDA(cudaStreamSynchronize(nm_ctx().stream));
+  }
+  void from_host(const std::vector<T>& h) { alloc(h.size()); upload(h.data(), h.size()); }
+  void download(T* h, size_t cnt) const {
+    if (cnt) NM_CUDA(cudaMemcpyAsync(h, p, cnt * sizeof(T), cudaMemcpyDeviceToHost, nm_ctx().stream));
+    NM_CUDA(cudaStreamSynchronize(nm_ctx().stream));
+  }
+  void zero() { if (n) NM_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), nm_ctx().stream)); }
+};
+
+// ---------------------------------------------------------------- distributed CSR
+enum NmFormat { NM_FMT_CSR = 0, NM_FMT_ROW3 = 1, NM_FMT_KRON3 = 2 };
+
+struct NmHalo {
+  int nghost = 0;                         // ghost columns, sorted by global id (= grouped by owner rank)
+  std::vector<int> ghost_glob;            // global column ids of the ghosts
+  std::vector<int> recv_cnt, recv_off;    // per peer, into the ghost tail
+  std::vector<int> send_cnt, send_off;    // per peer, into sendbuf
+  int nsend = 0;
+  DBuf<int> send_idx;                     // local (owned) column ids to pack, device
+  DBuf<double> sendbuf;                   // device
+  DBuf<double> xg;                        // ghost values, device (gather target c >= ncol -> xg[c-ncol])
+};
+
+struct NmParcsr {
+  int nrow_glob = 0, ncol_glob = 0;
+  int nrow = 0, ncol = 0;                 // local (owned) rows / columns
+  int row0 = 0, col0 = 0;                 // first global row / column owned
+  long long nnz = 0;
+  DBuf<int> ia, ja;                       // local CSR; ja in local column space (owned first, ghosts after)
+  DBuf<double> a;
+  int format = NM_FMT_CSR;
+  // ROW3: rows 3b..3b+2 share one column list made of aligned triples -> one block-column id per
+  //       triple (bja), values stay in CSR order.  KRON3: additionally M (x) I3 -> scalar values mval.
+  int nbrow = 0;
+  DBuf<int> bia, bja;
+  DBuf<double> mval;
+  NmHalo halo;
+  double avg_row = 0.0;                   // mean entries per (block-)row processed by one subwarp
+  long long fmt_bytes = 0;                // bytes one SpMV streams in the chosen format (matrix part)
+};
+
+// ---------------------------------------------------------------- ChebIter (B^-1, Ap^-1)
+struct NmChebIter {
+  NmParcsr* M = nullptr;
+  double lb = 0, ub = 0, theta = 0;
+  int deg = 0;
+  std::vector<double> ak, bk;             // d_{k+1} = ak d_k + bk r_{k+1}
+  DBuf<double> r, d0, d1;
+  long long nsolve = 0, nmatvec = 0;
+  double t_total = 0;
+};
+
+// ---------------------------------------------------------------- operators (the reference's callbacks)
+typedef void (*nm_matvec_fn)(double* x, double* y, void* data);
+enum NmOpKind { NM_OP_CSR = 0, NM_OP_SOLID = 1, NM_OP_FLUIDSOLID = 2, NM_OP_CALLBACK = 3 };
+
+struct NmOp {
+  int kind = NM_OP_CSR;
+  int n = 0;                               // local length of x and y
+  NmParcsr* M = nullptr;                   // NM_OP_CSR: borrowed
+  std::unique_ptr<NmParcsr> As, Es, ETs;   // scaled copies D A D, D E Dp, Dp ET D (owned)
+  NmChebIter* chebAp = nullptr;            // borrowed
+  DBuf<double> x1, y0, w1;                 // fluid work vectors (pressure, pressure, displacement)
+  nm_matvec_fn fn = nullptr;               // NM_OP_CALLBACK
+  void* fn_data = nullptr;
+  std::vector<double> hx, hy;
+  long long napply = 0;
+};
+
+// ---------------------------------------------------------------- filter polynomial
+struct NmPol {
+  int deg = 0, type = 0;
+  std::vector<double> mu;
+  double cc = 0, dd = 0, gam = 0, bar = 0;
+  double intv[4] = {0, 0, 0, 0};
+};
+
+// ---------------------------------------------------------------- solver context (pevsl handle)
+struct NmPevsl {
+  int N = 0, n = 0, nfirst = -1;
+  NmOp* A = nullptr;
+  NmOp* B = nullptr;
+  NmChebIter* bsol = nullptr;
+  bool geneig = false;
+  std::vector<std::unique_ptr<NmOp>> owned_ops;
+  // results of the last cheblannr
+  int nev = 0;
+  std::vector<double> lam, res;
+  DBuf<double> Y;                          // n x nev, column-major, B-orthonormal (scaled coordinates)
+  // statistics
+  int last_steps = 0, last_deg = 0;
+  double t_filter = 0, t_reorth = 0, t_total = 0, t_ritz = 0;
+  long long n_filter_apply = 0;
+  unsigned long long seed = 4321;
+};
+
+// ---------------------------------------------------------------- internal entry points
+// parcsr
+NmParcsr* nm_parcsr_build(int nrow_glob, int ncol_glob, const int* row_starts, const int* col_starts,
+                          const int* ia, const int* ja, const double* a);
+NmParcsr* nm_parcsr_scaled_copy(const NmParcsr& M, const double* drow_dev, const double* dcol_dev);
+void nm_halo_exchange(NmParcsr& M, const double* x);
+void nm_spmv(NmParcsr& M, const double* x, double* y);                 // y = M x   (device pointers)
+void nm_spmv_add(NmParcsr& M, const double* x, double* y);             // y += M x
+// chebiter
+NmChebIter* nm_chebiter_build(double lb, double ub, int deg, NmParcsr* M);
+void nm_chebiter_solve(NmChebIter& C, const double* b, double* x);
+// operators
+void nm_op_apply(NmOp& op, const double* x, double* y);
+// y-update of ChebAv fused into the operator: vout = t*(Op(w) - cc*vk) - vkm1 ; y (+)= mu*vout
+void nm_op_apply_filter(NmOp& op, const double* w, const double* vk, const double* vkm1, double* vout, double* y,
+                        double t, double cc, double mu, double mu0, int first);
+// vector kernels (all on nm_ctx().stream)
+void nm_vec_copy(double* dst, const double* src, size_t n);
+void nm_vec_set(double* dst, double v, size_t n);
+void nm_vec_scale(double* x, double s, size_t n);
+void nm_vec_mul(double* y, const double* x, const double* d, size_t n);      // y = x .* d
+void nm_vec_axpy(double* y, double a, const double* x, size_t n);
+void nm_vec_axpy_dev(double* y, const double* a_dev, double sign, const double* x, size_t n);  // y += sign*(*a)*x
+void nm_vec_dot_dev(const double* x, const double* y, size_t n, double* out_dev);              // allreduced
+double nm_vec_dot(const double* x, const double* y, size_t n);
+void nm_vec_random(double* x, size_t n, unsigned long long seed, unsigned long long offset);
+void nm_allreduce_sum(double* buf_dev, size_t n);
+void nm_filter_update(const double* vkm1, double* vout, const double* vk, const double* u, double* y, double t,
+                      double cc, double mu, double mu0, int first, size_t n);
+// host maths
+int nm_tridiag_eig(int k, const double* d, const double* e, double* w, double* Z /* k*k col-major or null */);
+int nm_tridiag_eig_ex(int k, const double* d, const double* e, double* w, double* Z, double* lastrow);
+void nm_findpol(const double xintv[4], double thresh_int, double thresh_ext, NmPol& pol);
+// solver
+void nm_lanbounds(NmPevsl& P, int mlan, int lanstep, double tol, double* lmin, double* lmax);
+void nm_cheblannr(NmPevsl& P, const double xintv[4], int maxit, double tol, const NmPol& pol);
+void nm_filter_apply(NmPevsl& P, const NmPol& pol, const double* z, double* y, double* work /* 3n */);
+
+static inline int nm_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }

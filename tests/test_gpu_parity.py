@@ -1,0 +1,299 @@
+"""GPU parity tests (run with -m gpu on the B200): the CUDA path, called through the C ABI, against the
+oracle on the same inputs and against the committed golden eigenvalues.
+
+Tolerances (floating point, fp64): a product y = A x may differ from the CPU's sequential sum by
+reassociation only: |dy_i| <= 64 * eps * sum_j |a_ij x_j|.  Eigenvalues: relative 1e-10 (north_star).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_case, to_coomat
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(float).eps
+
+
+@pytest.fixture(scope="module")
+def nm():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from normalmodes_b200 import _lib
+    L = _lib.lib()
+    _lib.check(L.nm_init(0))
+    return L
+
+
+def _spmv_tol(S, x):
+    return 64 * EPS * (abs(S) @ np.abs(x)) + 1e-300
+
+
+@pytest.mark.parametrize("name", ["const3k_p1_j1", "prem3k_p1_j2", "const3k_p2_j1", "prem3k_p2_j2"])
+def test_spmv_all_matrices(nm, name):
+    from oracle import fem
+    from normalmodes_b200 import matvec as mv
+    c = load_case(name)
+    rng = np.random.default_rng(12345)
+    expect_fmt = {"A": "ROW3", "Ad": "ROW3", "B": "KRON3"}
+    for k, m in to_coomat(c["mats"]).items():
+        S = fem.to_scipy(c["mats"][k])
+        h = mv.parcsr_create(m)
+        info = mv.parcsr_info(h)
+        assert info["nnz"] == S.nnz and info["nrow"] == S.shape[0] and info["ncol"] == S.shape[1]
+        if k in expect_fmt:
+            assert info["format"] == expect_fmt[k], (k, info)
+        x = rng.uniform(-1, 1, S.shape[1])
+        y = mv.parcsr_matvec(h, x, S.shape[0])
+        assert (np.abs(y - S @ x) <= _spmv_tol(S, x)).all(), k
+        nm.nm_parcsr_free(h)
+
+
+def test_spmv_forced_csr_and_edge_cases(nm):
+    """Generic CSR kernel: empty rows, a 1x1 matrix, a ragged random matrix, a rectangular one."""
+    import scipy.sparse as sp
+    from normalmodes_b200 import matvec as mv
+    rng = np.random.default_rng(7)
+    mats = [sp.csr_matrix(np.array([[2.5]])),
+            sp.random(257, 131, density=0.05, random_state=1, format="csr"),
+            sp.random(64, 64, density=0.5, random_state=2, format="csr"),
+            sp.csr_matrix((5, 9))]
+    lil = sp.random(300, 300, density=0.02, random_state=3, format="lil")
+    lil[17, :] = 0; lil[0, :] = rng.standard_normal(300)         # an empty row and a full row
+    mats.append(lil.tocsr())
+    for S in mats:
+        S.sort_indices()
+        m = mv.COOmat([0, S.shape[0]], S.indptr, S.indices, S.data, coldist=[0, S.shape[1]])
+        h = mv.parcsr_create(m)
+        x = rng.uniform(-1, 1, S.shape[1])
+        y = mv.parcsr_matvec(h, x, S.shape[0])
+        assert (np.abs(y - S @ x) <= _spmv_tol(S, x)).all()
+        nm.nm_parcsr_free(h)
+
+
+def test_row3_kron3_equal_forced_csr(nm, monkeypatch):
+    """The compressed formats and the plain CSR kernel agree to reassociation."""
+    from oracle import fem
+    from normalmodes_b200 import matvec as mv
+    c = load_case("const3k_p1_j1")
+    x = np.random.default_rng(5).uniform(-1, 1, c["num"]["N"])
+    ys = {}
+    for force in ("0", "1"):
+        monkeypatch.setenv("NM_FORCE_CSR", force)
+        for k, m in to_coomat(c["mats"]).items():
+            h = mv.parcsr_create(m)
+            assert (mv.parcsr_info(h)["format"] == "CSR") == (force == "1")
+            ys[(k, force)] = mv.parcsr_matvec(h, x, m.Gsiz)
+            nm.nm_parcsr_free(h)
+    for k in ("A", "B"):
+        S = fem.to_scipy(c["mats"][k])
+        assert (np.abs(ys[(k, "0")] - ys[(k, "1")]) <= 2 * _spmv_tol(S, x)).all()
+
+
+@pytest.mark.parametrize("name", ["const3k_p1_j1", "prem3k_p1_j2"])
+def test_jacobi_scaling_and_chebiter(nm, name):
+    from oracle import fem, solver
+    from normalmodes_b200 import matvec as mv
+    from normalmodes_b200._lib import check, dptr
+    c = load_case(name)
+    for key, sign in (("B", 1.0),) + ((("Ap", -1.0),) if "Ap" in c["mats"] else ()):
+        m = to_coomat(c["mats"])[key]
+        h = mv.parcsr_create(m)
+        d = np.empty(m.Gsiz)
+        check(nm.nm_parcsr_jacobi_scale(h, C.c_double(sign), dptr(d)))
+        ref, dref = fem.jacobi_scale(c["mats"][key], sign)
+        assert np.allclose(d, dref, rtol=4 * EPS, atol=0)
+        vals = np.empty(m.NNZ)
+        check(nm.nm_parcsr_get_values(h, dptr(vals)))
+        assert np.allclose(vals, ref["a"], rtol=8 * EPS, atol=0)
+        # Chebyshev solve against the oracle's, same bounds and degree
+        St = fem.to_scipy(ref)
+        lb, ub = solver.lanbounds(lambda v: St @ v, St.shape[0], 1000, 2000, 1e-12)
+        for deg in (1, 2, 25):
+            cheb = mv.chebiter_setup(lb, ub, deg, h)
+            b = np.random.default_rng(deg).standard_normal(St.shape[0])
+            x = mv.chebiter_solve(cheb, b)
+            xr = solver.chebiter(St, lb, ub, deg, b)
+            assert np.abs(x - xr).max() <= 1e-13 * np.abs(xr).max()
+            nm.nm_chebiter_free(cheb)
+        nm.nm_parcsr_free(h)
+
+
+@pytest.mark.parametrize("name", ["const3k_p1_j1", "prem3k_p1_j2", "const3k_p1_j2"])
+def test_setupmatvec_operators_and_bounds(nm, name):
+    """setupmatvec mirror: bounds of B~ (and Ap~), sparseAV / sparsefsAV / sparseBV against the oracle."""
+    from oracle import solver
+    from normalmodes_b200 import matvec as mv
+    c = load_case(name)
+    po = c["g"]["porder"]
+    ops = solver.Operators(c["mats"], po)
+    m = mv.setupmatvec(to_coomat(c["mats"]), po)
+    # LanTrbounds returns outer bounds: both implementations must enclose the spectrum and agree closely
+    assert abs(m.boundsB[0] - ops.boundsB[0]) < 1e-8 and abs(m.boundsB[1] - ops.boundsB[1]) < 1e-8
+    if ops.fluid:
+        assert abs(m.boundsAp[0] - ops.boundsAp[0]) < 1e-8 and abs(m.boundsAp[1] - ops.boundsAp[1]) < 1e-8
+    v = np.random.default_rng(11).standard_normal(ops.n)
+    wB = mv.sparseBV(v, m)
+    assert np.abs(wB - ops.bmv(v)).max() <= 1e-14 * np.abs(wB).max()
+    # same ChebIter bounds on both sides for the operator comparison
+    ops.boundsB = m.boundsB
+    if ops.fluid:
+        ops.boundsAp = m.boundsAp
+    wA = mv.sparseAV(v, m)
+    ref = ops.amv(v)
+    assert np.abs(wA - ref).max() <= 1e-12 * np.abs(ref).max()
+    xs = mv.solveBV(v, m)
+    assert np.abs(xs - ops.bsol(v)).max() <= 1e-13 * np.abs(xs).max()
+
+
+def _solve(name, **kw):
+    from normalmodes_b200 import matvec as mv, pevsl
+    c = load_case(name)
+    g = c["g"]
+    m = mv.setupmatvec(to_coomat(c["mats"]), g["porder"])
+    r = pevsl.pnm_apply_pevsl(m, g["lowfreq"], g["upfreq"], **kw)
+    return c, m, r
+
+
+def test_filter_application_matches_oracle(nm):
+    """One y = p(A B^-1) z (ChebAv, fused kernels) against the oracle's ChebAv with the same polynomial."""
+    from oracle import solver
+    from normalmodes_b200 import matvec as mv, pevsl
+    from normalmodes_b200._lib import check, dptr
+    c = load_case("prem3k_p1_j2")
+    ops = solver.Operators(c["mats"], 1)
+    m = mv.setupmatvec(to_coomat(c["mats"]), 1)
+    ops.boundsB, ops.boundsAp = m.boundsB, m.boundsAp
+    xintv = [3.9478420978080176e-07, 3.9478419801531574e-05, -4.677924941383012e-07, 0.02812179603432921]
+    ref_pol = solver.findpol(xintv, 0.8, 0.7)
+    pol = pevsl.Pol(xintv, 0.8, 0.7)
+    P = mv.Pevsl(m.Gpbsiz, m.pbsiz, 0)
+    P.setbmv_op(m.opB); P.setbsol_chebiter(m.chebB); P.setamv_op(m.opA); P.set_geneig()
+    z = np.random.default_rng(2).standard_normal(ops.n)
+    y = np.empty_like(z)
+    check(nm.nm_pevsl_filter_host(P.h, pol.h, dptr(z), dptr(y)))
+    yr = solver.chebav(ref_pol, z, ops)
+    assert np.abs(y - yr).max() <= 1e-10 * np.abs(yr).max()
+    P.finish()
+
+
+def test_solve_const3k_demo_config(nm, golden):
+    """BASELINE config 1: demos/global_conf (CONST3k, P1, JOB 1, 0.2-2.0 mHz): count exact, eigenvalues
+    1e-10 relative against the independent dense solve, B-orthonormal vectors, reference residual."""
+    from oracle import fem
+    from normalmodes_b200 import pevsl
+    c, m, r = _solve("const3k_p1_j1")
+    truth = np.array(c["g"]["truth_eigs"])
+    assert r.nev == len(truth) == 271
+    assert np.max(np.abs(r.eigval - truth) / truth) < 1e-10
+    Bs, d = fem.jacobi_scale(c["mats"]["B"])
+    Bt = fem.to_scipy(Bs)
+    Y = r.eigvec.T
+    G = Y.T @ (Bt @ Y)
+    assert np.abs(G - np.eye(r.nev)).max() < 1e-8
+    rel = pevsl.finalize_eigerr(r, m.Gpbsiz)
+    assert rel.max() < 1e-12                                   # the reference's own 'relative err.' (README: ~1e-13)
+    assert (r.res2 / np.abs(r.eigval)).max() < 1e-9            # plain 2-norm with the reference's degree-25 B-solve
+
+
+def test_solve_prem3k_fluid_solid(nm):
+    """Fluid outer core + reference gravity (JOB 2): Schur-complement operator, Ap ChebIter inside the filter."""
+    c, m, r = _solve("prem3k_p1_j2")
+    truth = np.array(c["g"]["truth_eigs"])
+    assert r.nev == len(truth)
+    assert np.max(np.abs(r.eigval - truth) / truth) < 1e-10
+
+
+def test_solve_tight_inner_degree_meets_plain_residual(nm):
+    """'tight' mode: inner degree 34 => plain ||A y - lam B y||_2/|lam| <= 1e-12."""
+    from normalmodes_b200 import matvec as mv, pevsl
+    c = load_case("const3k_p1_j1")
+    m = mv.setupmatvec(to_coomat(c["mats"]), 1, degB=36)
+    r = pevsl.pnm_apply_pevsl(m, 0.2, 2.0)
+    assert r.nev == 271
+    assert (r.res2 / np.abs(r.eigval)).max() <= 1e-12
+
+
+def test_f90_abi_with_host_callbacks(nm):
+    """The reference's own calling sequence through the pevsl_*_f90_ symbols: every argument by reference,
+    operators supplied as HOST callbacks (the unmodified mod_matvec.f90 contract)."""
+    from oracle import fem, solver
+    c = load_case("const3k_p1_j1")
+    mats = c["mats"]
+    Bs, d = fem.jacobi_scale(mats["B"])
+    n = c["num"]["N"]
+    i4 = lambda v: C.byref(C.c_int32(v))
+    f8 = lambda v: C.byref(C.c_double(v))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    comm = C.c_int32(0)
+    starts = np.array([0, n], dtype=np.int32)
+
+    def create(m):
+        h = C.c_uint64(0)
+        ia = m["ia"].astype(np.int32); ja = m["ja"].astype(np.int32); a = np.ascontiguousarray(m["a"])
+        nm.pevsl_parcsrcreate_f90_(i4(n), i4(n), ip(starts), ip(starts), ip(ia), ip(ja), dp(a), C.byref(comm), C.byref(h))
+        return h
+    sBV, sAV = create(Bs), create(mats["A"])
+    CB = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+
+    def bmv(x, y, data):
+        nm.pevsl_parcsrmatvec_f90_(x, y, C.byref(sBV))
+
+    def amv(x, y, data):                                       # sparseAV: v0 = v*d ; w0 = A v0 ; w = w0*d
+        v0 = np.ctypeslib.as_array(x, (n,)) * d
+        w0 = np.empty(n)
+        nm.pevsl_parcsrmatvec_f90_(dp(v0), dp(w0), C.byref(sAV))
+        np.ctypeslib.as_array(y, (n,))[:] = w0 * d
+    cb_b, cb_a = CB(bmv), CB(amv)
+    # setupmatvec: bounds of B~, ChebIter
+    pB = C.c_uint64(0)
+    nm.pevsl_start_f90_(C.byref(comm), C.byref(pB))
+    nm.pevsl_setprobsizes_f90_(C.byref(pB), i4(n), i4(n), i4(-1))
+    nm.pevsl_setamv_f90_(C.byref(pB), cb_b, None)
+    lmin, lmax = C.c_double(), C.c_double()
+    nm.pevsl_lanbounds_f90_(C.byref(pB), i4(1000), i4(2000), f8(1e-12), C.byref(lmin), C.byref(lmax))
+    assert 0.55 < lmin.value < 0.57 and abs(lmax.value - 2.5) < 1e-6
+    cheb = C.c_uint64(0)
+    nm.pevsl_setup_chebiter_f90_(C.byref(lmin), C.byref(lmax), i4(25), C.byref(sBV), C.byref(cheb))
+    nm.pevsl_finish_f90_(C.byref(pB))
+    b = np.random.default_rng(1).standard_normal(n); x = np.empty(n)
+    nm.pevsl_chebiter_f90_(i4(2), dp(b), dp(x), C.byref(cheb))
+    St = fem.to_scipy(Bs)
+    assert np.linalg.norm(b - St @ x) / np.linalg.norm(b) < 2e-11
+    # pnm_apply_pevsl on a narrow band (host callbacks bounce every vector: keep it short)
+    pAB = C.c_uint64(0)
+    nm.pevsl_start_f90_(C.byref(comm), C.byref(pAB))
+    nm.pevsl_setprobsizes_f90_(C.byref(pAB), i4(n), i4(n), i4(-1))
+    nm.pevsl_setbmv_f90_(C.byref(pAB), cb_b, None)
+    nm.pevsl_setbsol_chebiter_f90_(C.byref(pAB), i4(2), C.byref(cheb))
+    nm.pevsl_setamv_f90_(C.byref(pAB), cb_a, None)
+    nm.pevsl_set_geneig_f90_(C.byref(pAB))
+    nm.pevsl_lanbounds_f90_(C.byref(pAB), i4(3000), i4(5000), f8(1e-5), C.byref(lmin), C.byref(lmax))
+    a_, b_ = solver.freq_interval(0.2, 0.45, lmin.value)
+    xintv = np.array([a_, b_, lmin.value, lmax.value])
+    pol = C.c_uint64(0)
+    nm.pevsl_findpol_f90_(dp(xintv), f8(0.8), f8(0.7), C.byref(pol))
+    nm.pevsl_cheblannr_f90_(C.byref(pAB), dp(xintv), i4(9624), f8(1e-5), C.byref(pol))
+    nev = C.c_int32(0)
+    nm.pevsl_get_nev_f90_(C.byref(pAB), C.byref(nev))
+    truth = np.array(c["g"]["truth_eigs"]); truth = truth[(truth >= a_) & (truth <= b_)]
+    assert nev.value == len(truth) == 10
+    vals = np.empty(nev.value); vecs = np.empty(nev.value * n)
+    nm.pevsl_copy_result_f90_(C.byref(pAB), dp(vals), dp(vecs), i4(n))
+    assert np.max(np.abs(np.sort(vals) - truth) / truth) < 1e-10
+    nm.pevsl_chebiterstatsprint_f90_(C.byref(cheb))
+    nm.pevsl_freepol_f90_(C.byref(pol))
+    nm.pevsl_finish_f90_(C.byref(pAB))
+
+
+def test_error_paths(nm):
+    """Bad input is reported through the status + message, not a crash."""
+    from normalmodes_b200 import matvec as mv
+    from normalmodes_b200._lib import NmError
+    with pytest.raises(NmError):                                # 1-based column ids (forgot the col-1 of :59)
+        mv.parcsr_create(mv.COOmat([0, 2], [0, 1, 2], [1, 2], [1.0, 1.0]))
+    with pytest.raises(NmError):                                # ChebIter on an indefinite interval
+        h = mv.parcsr_create(mv.COOmat([0, 2], [0, 1, 2], [0, 1], [1.0, 1.0]))
+        mv.chebiter_setup(-1.0, 2.0, 5, h)

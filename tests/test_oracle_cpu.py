@@ -1,0 +1,165 @@
+"""CPU suite: the oracle against the committed golden vectors, host maths of the library, and the
+C-ABI surface (library loads and exports every declared symbol; no compute calls without a GPU)."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import load_case
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+CASES_FAST = ["const3k_p1_j1", "const3k_p1_j2", "prem3k_p1_j2", "rtmdwak8k_p1_j2", "const3k_p2_j1", "prem3k_p2_j2"]
+
+
+@pytest.mark.parametrize("name", CASES_FAST)
+def test_oracle_assembly_matches_golden(name):
+    """CSR pattern + DOF numbering integer-exact, values to rounding (same machine arithmetic)."""
+    c = load_case(name)
+    g = c["g"]
+    assert c["num"]["N"] == g["N"] and c["num"]["Np"] == g["Np"]
+    for k, gm in g["matrices"].items():
+        m = c["mats"][k]
+        assert list(m["shape"]) == gm["shape"] and m["ja"].size == gm["nnz"]
+        assert _sha(m["ia"].astype(np.int32)) == gm["ia_sha256"]
+        assert _sha(m["ja"].astype(np.int32)) == gm["ja_sha256"]
+        assert np.isclose(m["a"].sum(), gm["sum"], rtol=1e-9, atol=1e-9 * gm["abssum"])
+        assert np.isclose(np.abs(m["a"]).sum(), gm["abssum"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["const3k_p1_j1", "prem3k_p1_j2", "const3k_p2_j1"])
+def test_oracle_invariants(name):
+    """symmetry, B SPD (positive diagonal + diagonally scaled spectrum in (0, 5)), ET = E^T,
+    rigid-body null space of A for the solid JOB 1 model."""
+    from oracle import fem
+    c = load_case(name)
+    mats = c["mats"]
+    B = fem.to_scipy(mats["B"])
+    assert abs(B - B.T).max() <= 1e-12 * abs(B).max()
+    assert (B.diagonal() > 0).all()
+    if "A" in mats:
+        A = fem.to_scipy(mats["A"])
+        assert abs(A - A.T).max() <= 1e-9 * abs(A).max()
+        if c["g"]["job"] == 1 and c["g"]["porder"] == 1:
+            X = c["mesh"]["node"]
+            n = X.shape[0]
+            for comp in range(3):                      # translations
+                t = np.zeros((n, 3)); t[:, comp] = 1.0
+                assert np.abs(A @ t.ravel()).max() <= 1e-7 * abs(A).max()
+            for ax in range(3):                        # rotations
+                w = np.zeros(3); w[ax] = 1.0
+                r = np.cross(np.broadcast_to(w, X.shape), X)
+                assert np.abs(A @ r.ravel()).max() <= 1e-7 * abs(A).max() * np.abs(X).max()
+    else:
+        E = fem.to_scipy(mats["E"]); ET = fem.to_scipy(mats["ET"])
+        assert abs(E - ET.T).max() == 0.0
+        Ap = fem.to_scipy(mats["Ap"])
+        assert (Ap.diagonal() < 0).all()
+
+
+def test_oracle_filtered_lanczos_vs_truth(golden):
+    """The oracle's restatement of the pEVSL path finds every eigenvalue of the independent dense solve
+    (count exact, 1e-10 relative) on the reference's own demo configuration (demos/global_conf)."""
+    from oracle import solver
+    c = load_case("const3k_p1_j1")
+    g = c["g"]
+    ops, lam, Y, res, info = solver.solve(c["mats"], 1, g["lowfreq"], g["upfreq"])
+    truth = np.array(g["truth_eigs"])
+    assert len(lam) == len(truth) == 271
+    assert np.max(np.abs(lam - truth) / truth) < 1e-10
+    # B-orthonormality and the reference's RMS residual (README: "typically around 1e-13")
+    G = Y.T @ (ops.Bt @ Y)
+    assert np.abs(G - np.eye(len(lam))).max() < 1e-8
+    rms = max(solver.residual_rms(ops, lam[i], Y[:, i]) for i in range(0, len(lam), 10))
+    assert rms < 1e-12
+
+
+def test_oracle_chebiter_accuracy():
+    """App. D table: degree-25 Chebyshev solve of the P1 Jacobi-scaled mass matrix is ~1e-11 accurate."""
+    from oracle import solver, fem
+    c = load_case("const3k_p1_j1")
+    Bs, d = fem.jacobi_scale(c["mats"]["B"])
+    Bt = fem.to_scipy(Bs)
+    lb, ub = solver.lanbounds(lambda v: Bt @ v, Bt.shape[0], 1000, 2000, 1e-12)
+    assert 0.55 < lb < 0.57 and abs(ub - 2.5) < 1e-6
+    b = np.random.default_rng(0).standard_normal(Bt.shape[0])
+    x = solver.chebiter(Bt, lb, ub, 25, b)
+    r = np.linalg.norm(b - Bt @ x) / np.linalg.norm(b)
+    assert r < 2e-11
+
+
+def test_freq_interval_float32_semantics():
+    from oracle import solver
+    from normalmodes_b200 import pevsl
+    a, b = solver.freq_interval(0.2, 2.0, -1.0)
+    assert abs(a - 1.579136839123207e-06) < 1e-20 and abs(b - 0.0001579136792061263) < 1e-18
+    assert pevsl.freq_interval(0.2, 2.0, -1.0) == (a, b)
+    assert solver.freq_interval(0.0, 1.0, -3.0)[0] == -3.0
+
+
+# ------------------------------------------------------------------ library surface (no GPU needed)
+def test_library_builds_and_exports_declared_symbols():
+    from normalmodes_b200 import _lib
+    L = _lib.lib()
+    names = _lib.declared_symbols()
+    assert len(names) > 60
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    for n in ["pevsl_start_f90_", "pevsl_parcsrcreate_f90_", "pevsl_parcsrmatvec_f90_", "pevsl_cheblannr_f90_",
+              "pevsl_copy_result_f90_", "pevsl_setup_chebiter_f90_", "pevsl_chebiter_f90_", "pevsl_lanbounds_f90_",
+              "pevsl_findpol_f90_", "pevsl_freepol_f90_", "pevsl_finish_f90_", "pevsl_setamv_f90_", "pevsl_setbmv_f90_",
+              "pevsl_setbsol_chebiter_f90_", "pevsl_set_geneig_f90_", "pevsl_get_nev_f90_", "pevsl_setprobsizes_f90_",
+              "pevsl_chebiterstatsprint_f90_"]:
+        assert n in names
+
+
+def test_findpol_host_matches_oracle():
+    """nm_findpol (host C++) against the oracle's find_pol: same degree, same coefficients."""
+    from oracle import solver
+    from normalmodes_b200 import pevsl
+    for xintv in ([1.579136839123207e-06, 0.0001579136792061263, -2.77e-08, 0.0028953701550054407],
+                  [3.9478420978080176e-07, 3.9478419801531574e-05, -4.677924941383012e-07, 0.02812179603432921],
+                  [-1.0e-8, 2.0e-5, -1.0e-8, 3.0e-3],          # touches the left end
+                  [2.0e-3, 3.0e-3, -1.0e-8, 3.0e-3]):           # touches the right end
+        ref = solver.findpol(xintv, 0.8, 0.7)
+        pol = pevsl.Pol(xintv, 0.8, 0.7)
+        assert pol.deg == ref["deg"]
+        assert np.allclose(pol.mu, ref["mu"], rtol=1e-11, atol=1e-13)
+        assert abs(pol.bar - ref["bar"]) < 1e-11 and abs(pol.gam - ref["gam"]) < 1e-11
+        assert abs(pol.cc - ref["cc"]) <= 1e-18 and abs(pol.dd - ref["dd"]) <= 1e-18
+        pol.free()
+
+
+def test_tridiag_host_matches_lapack():
+    import scipy.linalg as sla
+    from normalmodes_b200._lib import lib, check, dptr
+    rng = np.random.default_rng(3)
+    for k in (1, 2, 7, 150):
+        d = rng.standard_normal(k); e = rng.standard_normal(max(k - 1, 1))
+        w = np.empty(k); Z = np.empty((k, k)); lr = np.empty(k)
+        check(lib().nm_tridiag_eig_host(k, dptr(d), dptr(e), dptr(w), dptr(Z), dptr(lr)))
+        if k == 1:
+            assert w[0] == d[0]; continue
+        wr, Vr = sla.eigh_tridiagonal(d, e[:k - 1])
+        assert np.allclose(w, wr, atol=1e-12)
+        V = Z.T                                                 # column-major k*k -> V[:, j]
+        T = np.diag(d) + np.diag(e[:k - 1], 1) + np.diag(e[:k - 1], -1)
+        assert np.abs(T @ V - V * w).max() < 1e-11
+        assert np.allclose(np.abs(lr), np.abs(V[-1, :]), atol=1e-11)
+
+
+def test_error_reporting_without_gpu():
+    """A compute call on a box without a CUDA device must fail loudly, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from normalmodes_b200._lib import lib
+    L = lib()
+    h = C.c_void_p()
+    rc = L.nm_pevsl_create(C.byref(h))
+    assert rc != 0
+    assert b"no CPU fallback" in L.nm_last_error_message()
