@@ -73,6 +73,29 @@ int nm_pol_coeffs(void* pol, double* mu /* deg+1 */);
 int nm_pol_free(void* pol);
 int nm_tridiag_eig_host(int k, const double* d, const double* e, double* w, double* Z, double* lastrow);
 
+/* ---- FE assembly: cg_create_matrix (mod_cg_create_matrix.f90:35-61) ----
+ * nm_fem_create  = topology + DOF numbering + CSR patterns on the host (matrixstruct :1269-1455,
+ *                  matrixstruct_general :1458-2033; vstat/v2v/P2 edge nodes of mod_geometry.f90:284-689);
+ *                  integer-exact with the reference for a given part[] (NULL: nproc = 1).  No GPU needed.
+ * nm_fem_assemble_values = element integration + scatter on the device (CGE3D_ISO :980-1266,
+ *                  CGFSE3D_ISO :103-977).  Inputs in the reference's file layout but
+ *                  0-based: ele/neigh [ntet][4] (neigh -1 = boundary), node [nvert][3],
+ *                  vp/vs/rho [ntet][pNp], g0 [ntet][pNp][3] in m/s^2 (JOB >= 2).
+ * matrix ids: 0 = A (Ad in the fluid case), 1 = B, 2 = E, 3 = ET, 4 = Ap (CGM%Ap, i.e. before the sign flip
+ * of mod_matvec.f90:137).  Columns are 0-based global ids, rows are this rank's rows. */
+int nm_fem_create(int ntet, int nvert, const int* ele, const int* neigh, const double* node, int porder,
+                  const double* vs, int nproc, const int* part /* [nn] or NULL */, int rank, void** fem_out);
+int nm_fem_free(void* fem);
+int nm_fem_info(void* fem, int* nn, int* N, int* Np, int* fluidcase, int* n_local_elements);
+int nm_fem_matrix_sizes(void* fem, int which, int* present, int* nrow_local, long long* nnz_local);
+int nm_fem_matrix_get(void* fem, int which, int* rowdist, int* coldist, int* ia, int* ja, double* val);
+int nm_fem_numbering(void* fem, int* vstat, int* vnum, int* pnum, int* vstt, int* pstt, int* order);
+int nm_fem_t2n(void* fem, int* t2n);
+/* reference-element matrices (host): M [pNp^2], D [3][pNp^2], MF [4][Nfp^2], Fmask [4][Nfp] (src/mod_geometry.f90:2307-2523) */
+int nm_refelem_get(int porder, double* M, double* D, double* MF, int* Fmask);
+int nm_fem_assemble_values(void* fem, int job, const double* vp, const double* vs, const double* rho,
+                           const double* g0);
+
 /* ---- solver context: pevsl_start .. pevsl_copy_result (mod_pevsl.f90:54-130) ---- */
 int nm_pevsl_create(void** pevsl_out);
 int nm_pevsl_free(void* pevsl);

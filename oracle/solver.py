@@ -413,13 +413,19 @@ def truth_eigs(mats, a, b, dense_limit=6000):
         # [Ad E; ET Ap][u;p] = lam [B 0; 0 0][u;p], whose finite eigenvalues are those of the Schur complement
         Ad = fem.to_scipy(mats["Ad"]); E = fem.to_scipy(mats["E"]); ET = fem.to_scipy(mats["ET"])
         Ap = fem.to_scipy(mats["Ap"]); Bm = fem.to_scipy(mats["B"])
-        K = sp.bmat([[Ad, E], [ET, Ap]], format="csc")
-        K = ((K + K.T) / 2.0).tocsc()
-        Mm = sp.block_diag([Bm, sp.csr_matrix(Ap.shape)], format="csc")
         sigma = (a + b) / 2.0
+        K = sp.bmat([[Ad - sigma * Bm, E], [ET, Ap]], format="csc")
+        lu = spla.splu(K)
+        npr = Ap.shape[0]
+
+        def opinv(rhs):                      # (A_eff - sigma B)^-1 rhs through the augmented LU
+            return lu.solve(np.concatenate([rhs, np.zeros(npr)]))[:n]
+        OPinv = spla.LinearOperator((n, n), matvec=opinv, dtype=float)
+        Aop = spla.LinearOperator((n, n), matvec=lambda v: v, dtype=float)   # unused in shift-invert mode
         k = 64
         while True:
-            w = spla.eigsh(K, k=min(k, n - 2), M=Mm, sigma=sigma, which="LM", return_eigenvectors=False)
+            w = spla.eigsh(Aop, k=min(k, n - 2), M=Bm.tocsc(), sigma=sigma, which="LM", OPinv=OPinv,
+                           return_eigenvectors=False)
             w = np.sort(w)
             if (w.min() < a and w.max() > b) or k >= n - 2:
                 return w[(w >= a) & (w <= b)]
