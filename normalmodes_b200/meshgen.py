@@ -1,10 +1,12 @@
 """Builder-generated PREM-like planet models for the benchmark configs (BASELINE.json configs 2-5).
 
-PlanetaryModels / TetGen are not available offline, so the mesh is built here: a jittered BCC point
-lattice inside the ball plus Fibonacci point shells on the free surface and on the two PREM
-discontinuities kept by the reference's `prem_3L` models (ICB 1221.5 km, CMB 3480 km), tetrahedralised
-with Qhull (scipy.spatial.Delaunay).  Elements are classified by centroid radius into inner core
-(solid) / outer core (fluid, vs = 0) / mantle+crust (solid), so fluid-solid interfaces are mesh faces.
+PlanetaryModels / TetGen are not available offline, so the mesh is built here: a conforming cubed-sphere
+grid (central cube + 6 equiangular radial chunks) whose grid surfaces include the free surface and the two
+PREM discontinuities kept by the reference's `prem_3L` models (ICB 1221.5 km, CMB 3480 km), every
+hexahedron cut into 12 tetrahedra.  Elements are classified by centroid radius into inner core (solid) /
+outer core (fluid, vs = 0) / mantle+crust (solid); the fluid-solid interfaces are triangulated spheres, so
+every mesh edge joining two interface vertices lies ON the interface -- which the reference's P2 edge-node
+status rule (src/mod_geometry.f90:672-680) silently requires.
 Material values are PREM's polynomials (Dziewonski & Anderson 1981, isotropic, ocean replaced by upper
 crust) evaluated at the element nodes inside the element's own layer; the reference gravity
 g0 = -g(r) r^ (m/s^2, as the reference's *_potential_acceleration_true.dat files) comes from the radial
@@ -66,70 +68,113 @@ def gravity_profile(nr=20001):
     return r, g
 
 
-def _fibonacci_sphere(n, radius):
-    i = np.arange(n) + 0.5
-    phi = np.arccos(1.0 - 2.0 * i / n)
-    th = np.pi * (1.0 + 5.0 ** 0.5) * i
-    return radius * np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], axis=1)
+def _face_neighbours(ele):
+    """neigh[k, j] = element sharing the face opposite local vertex j (-1: boundary)."""
+    ne = ele.shape[0]
+    faces = np.stack([np.delete(ele, j, axis=1) for j in range(4)], axis=1).reshape(-1, 3)   # row 4k+j
+    fs = np.sort(faces, axis=1)
+    o = np.lexsort((fs[:, 2], fs[:, 1], fs[:, 0]))
+    f = fs[o]
+    same = (f[1:] == f[:-1]).all(axis=1)
+    neigh = np.full(4 * ne, -1, dtype=np.int64)
+    a = o[:-1][same]; b = o[1:][same]
+    neigh[a] = b // 4; neigh[b] = a // 4
+    return neigh.reshape(ne, 4)
+
+
+def _radial_levels(nx):
+    """Radii of the spherical grid surfaces from the ICB outwards (ICB, CMB and the free surface are grid
+    surfaces), spaced like the lateral cell size at the middle of each shell."""
+    levels = [R_ICB]
+    for lo, hi in ((R_ICB, R_CMB), (R_CMB, R_EARTH)):
+        lateral = 0.5 * np.pi * 0.5 * (lo + hi) / nx
+        n = max(1, int(round((hi - lo) / lateral)))
+        levels += list(lo + (hi - lo) * np.arange(1, n + 1) / n)
+    return np.array(levels)
+
+
+def _count_tets(nx):
+    c = 0.45 * R_ICB
+    ncore = max(1, int(round((R_ICB - c) / (0.5 * np.pi * 0.75 * R_ICB / nx))))
+    return 12 * (nx ** 3 + 6 * nx * nx * (ncore + len(_radial_levels(nx)) - 1)), ncore
 
 
 def build_mesh(ntet_target, seed=0):
-    """Tetrahedral mesh of the ball with ~ntet_target elements.  Returns dict(ele, neigh, node), 0-based,
-    positively oriented, neigh[k, j] = element across the face opposite local vertex j (-1 boundary)."""
-    from scipy.spatial import Delaunay
-    rng = np.random.default_rng(seed)
-    npts = max(ntet_target / 6.2, 60.0)
-    a = (2.0 * (4.0 / 3.0) * np.pi * R_EARTH ** 3 / npts) ** (1.0 / 3.0)      # BCC cell: 2 points per a^3
-    m = int(np.ceil(R_EARTH / a)) + 1
-    g = np.arange(-m, m + 1) * a
-    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
-    P = np.concatenate([np.stack([X, Y, Z], -1).reshape(-1, 3), np.stack([X, Y, Z], -1).reshape(-1, 3) + a / 2.0])
-    P = P + rng.uniform(-0.02 * a, 0.02 * a, P.shape)
-    r = np.linalg.norm(P, axis=1)
-    s = 0.87 * a                                                               # nearest-neighbour distance of BCC
-    keep = r < R_EARTH - 0.45 * s
-    for rs in (R_ICB, R_CMB):
-        keep &= np.abs(r - rs) > 0.4 * s
-    shells = [P[keep]]
-    for rs in (R_ICB, R_CMB, R_EARTH):
-        n = max(int(4.0 * np.pi * rs ** 2 / (0.866 * s * s)), 12)
-        shells.append(_fibonacci_sphere(n, rs))
-    node = np.concatenate(shells)
-    node = node[rng.permutation(node.shape[0])]                               # unstructured numbering, like TetGen's
-    tri = Delaunay(node)
-    ele = tri.simplices.astype(np.int64)
-    neigh = tri.neighbors.astype(np.int64)
-    # positive orientation (reference meshes: all detJ > 0, SURVEY App. A)
+    """Conforming tetrahedral mesh of the ball with ~ntet_target elements: a cubed sphere (central cube +
+    6 radial chunks, equiangular) whose grid surfaces include the ICB, the CMB and the free surface, every
+    hexahedron cut into 6 pyramids around its centre and every pyramid into 2 tets along the base diagonal
+    through the lowest-numbered vertex (so neighbouring hexahedra agree).  Returns dict(ele, neigh, node),
+    0-based, positively oriented, neigh[k, j] = element across the face opposite local vertex j (-1 boundary)."""
+    nx = 2
+    while _count_tets(nx + 1)[0] <= ntet_target * 1.05:
+        nx += 1
+    _, ncore = _count_tets(nx)
+    c = 0.45 * R_ICB
+    ang = np.tan(np.linspace(-1.0, 1.0, nx + 1) * np.pi / 4.0)
+    pts = []; hexes = []; off = 0
+
+    def add_block(P):                      # P: (n0+1, n1+1, n2+1, 3) structured points -> hexes
+        nonlocal off
+        n0, n1, n2 = P.shape[0] - 1, P.shape[1] - 1, P.shape[2] - 1
+        idx = (np.arange(P.shape[0] * P.shape[1] * P.shape[2]) + off).reshape(P.shape[:3])
+        off += idx.size
+        pts.append(P.reshape(-1, 3))
+        h = np.stack([idx[:-1, :-1, :-1], idx[1:, :-1, :-1], idx[1:, 1:, :-1], idx[:-1, 1:, :-1],
+                      idx[:-1, :-1, 1:], idx[1:, :-1, 1:], idx[1:, 1:, 1:], idx[:-1, 1:, 1:]], axis=-1)
+        hexes.append(h.reshape(-1, 8))
+    # central cube
+    X, Y, Z = np.meshgrid(c * ang, c * ang, c * ang, indexing="ij")
+    add_block(np.stack([X, Y, Z], -1))
+    # six chunks: (u, v) on the cube face, w radial level
+    U, V = np.meshgrid(ang, ang, indexing="ij")
+    one = np.ones_like(U)
+    faces = [np.stack([U, V, one], -1), np.stack([U, V, -one], -1), np.stack([U, one, V], -1),
+             np.stack([U, -one, V], -1), np.stack([one, U, V], -1), np.stack([-one, U, V], -1)]
+    shells = _radial_levels(nx)
+    for Fc in faces:
+        d = Fc / np.linalg.norm(Fc, axis=-1, keepdims=True)
+        lev = [(1.0 - t) * c * Fc + t * R_ICB * d for t in np.arange(0, ncore) / ncore]
+        lev += [r * d for r in shells]
+        add_block(np.stack(lev, axis=2))
+    P = np.concatenate(pts); H = np.concatenate(hexes)
+    # merge coincident vertices (chunk edges / cube faces)
+    key = np.round(P / 1.0e-5).astype(np.int64)
+    _, first, inv = np.unique(key, axis=0, return_index=True, return_inverse=True)
+    node = P[first]; H = inv.reshape(-1)[H]
+    nv = node.shape[0]
+    # spatially coherent vertex numbering (coarse grid, z-major), as mesh generators usually emit
+    a = (4.0 / 3.0 * np.pi * R_EARTH ** 3 / max(nv, 1)) ** (1.0 / 3.0)
+    g = np.floor((node + R_EARTH) / (4.0 * a)).astype(np.int64)
+    order = np.lexsort((node[:, 0], g[:, 0], g[:, 1], g[:, 2]))
+    rank = np.empty(nv, dtype=np.int64); rank[order] = np.arange(nv)
+    node = node[order]; H = rank[H]
+    # hexahedron -> 6 pyramids around the centre -> 12 tets
+    cen = node[H].mean(axis=1)
+    cid = nv + np.arange(H.shape[0])
+    node = np.concatenate([node, cen])
+    quads = np.array([[0, 1, 2, 3], [4, 5, 6, 7], [0, 1, 5, 4], [3, 2, 6, 7], [0, 3, 7, 4], [1, 2, 6, 5]])
+    tets = []
+    for q in quads:
+        Q = H[:, q]                                                   # cyclic corner order
+        k = np.argmin(Q, axis=1)
+        even = (k % 2 == 0)[:, None]
+        t1 = np.where(even, np.stack([Q[:, 0], Q[:, 1], Q[:, 2], cid], 1), np.stack([Q[:, 1], Q[:, 2], Q[:, 3], cid], 1))
+        t2 = np.where(even, np.stack([Q[:, 0], Q[:, 2], Q[:, 3], cid], 1), np.stack([Q[:, 1], Q[:, 3], Q[:, 0], cid], 1))
+        tets += [t1, t2]
+    ele = np.concatenate(tets).astype(np.int64)
+    # interleave so that the 12 tets of a hexahedron are consecutive (element locality)
+    nh = H.shape[0]
+    ele = ele.reshape(12, nh, 4).transpose(1, 0, 2).reshape(-1, 4)
     Xe = node[ele]
-    B = Xe[:, 1:4, :] - Xe[:, 0:1, :]
-    det = np.linalg.det(B)
+    det = np.linalg.det(Xe[:, 1:4, :] - Xe[:, 0:1, :])
     flip = det < 0
     ele[flip, 0], ele[flip, 1] = ele[flip, 1].copy(), ele[flip, 0].copy()
-    neigh[flip, 0], neigh[flip, 1] = neigh[flip, 1].copy(), neigh[flip, 0].copy()
-    # drop zero-volume hull slivers (4 nearly coplanar surface points); only boundary elements qualify
-    vol = np.abs(det) / 6.0
-    bad = (vol < 1e-6 * a ** 3) & (neigh < 0).any(axis=1)
-    if bad.any():
-        newid = np.cumsum(~bad) - 1
-        ele = ele[~bad]
-        neigh = neigh[~bad]
-        neigh = np.where(neigh >= 0, np.where(bad[np.maximum(neigh, 0)], -1, newid[np.maximum(neigh, 0)]), -1)
-    used = np.zeros(node.shape[0], dtype=bool); used[ele.ravel()] = True
-    if not used.all():
-        newv = np.cumsum(used) - 1
-        node = node[used]; ele = newv[ele]
-    # cache-friendly numbering: order vertices along a coarse spatial grid (Morton-like), as mesh
-    # generators' output usually is; the DOF numbering contract is "whatever ids the input files carry"
-    key = np.floor((node + R_EARTH) / (4.0 * a)).astype(np.int64)
-    order = np.lexsort((key[:, 0], key[:, 1], key[:, 2]))
-    inv = np.empty_like(order); inv[order] = np.arange(order.size)
-    node = node[order]; ele = inv[ele]
-    cent = node[ele].mean(axis=1)
-    eo = np.lexsort((cent[:, 0], cent[:, 1], cent[:, 2]))
-    einv = np.empty_like(eo); einv[eo] = np.arange(eo.size)
-    ele = ele[eo]; neigh = neigh[eo]
-    neigh = np.where(neigh >= 0, einv[np.maximum(neigh, 0)], -1)
-    return dict(ntet=int(ele.shape[0]), nvert=int(node.shape[0]), ele=ele, neigh=neigh, node=node, spacing=a)
+    # elements ordered like their hexahedra's centres (z-major coarse grid)
+    hc = np.floor((cen + R_EARTH) / (4.0 * a)).astype(np.int64)
+    ho = np.lexsort((cen[:, 0], hc[:, 0], hc[:, 1], hc[:, 2]))
+    ele = ele.reshape(nh, 12, 4)[ho].reshape(-1, 4)
+    neigh = _face_neighbours(ele)
+    return dict(ntet=int(ele.shape[0]), nvert=int(node.shape[0]), ele=ele, neigh=neigh, node=node, nx=nx)
 
 
 _P2_PAIRS = np.array([[0, 1], [0, 2], [1, 2], [0, 3], [1, 3], [2, 3]])       # e12,e13,e23,e14,e24,e34

@@ -163,3 +163,30 @@ def test_error_reporting_without_gpu():
     rc = L.nm_pevsl_create(C.byref(h))
     assert rc != 0
     assert b"no CPU fallback" in L.nm_last_error_message()
+
+
+@pytest.mark.parametrize("name", ["const3k_p1_j1", "prem3k_p1_j2"])
+def test_c_port_matches_numpy_oracle(name):
+    """oracle/c (the CPU baseline bench.py times) against oracle/solver.py: operator, B-solve, ChebAv."""
+    from oracle import cpu as ocpu, fem, solver
+    c = load_case(name)
+    mats = c["mats"]
+    ops = solver.Operators(mats, 1)
+    Bs, d = fem.jacobi_scale(mats["B"])
+    t = lambda m: (m["ia"], m["ja"], m["a"])
+    if ops.fluid:
+        Aps, dp = fem.jacobi_scale(mats["Ap"], -1.0)
+        co = ocpu.CpuOps(t(Bs), t(mats["Ad"]), d, ops.boundsB, ops.degB, E=t(mats["E"]), ET=t(mats["ET"]), Ap=t(Aps), dp=dp,
+                         boundsAp=ops.boundsAp, degAp=ops.degAp)
+    else:
+        co = ocpu.CpuOps(t(Bs), t(mats["A"]), d, ops.boundsB, ops.degB)
+    v = np.random.default_rng(0).standard_normal(ops.n)
+    ref = ops.amv(v)
+    assert np.abs(co.apply_A(v) - ref).max() <= 1e-13 * np.abs(ref).max()
+    ref = ops.bsol(v)
+    assert np.abs(co.bsol(v) - ref).max() <= 1e-13 * np.abs(ref).max()
+    pol = solver.findpol([4e-7, 4e-5, -1e-8, 3e-3], 0.8, 0.7)
+    pol["deg"] = min(pol["deg"], 6); pol["mu"] = pol["mu"][:pol["deg"] + 1]
+    ref = solver.chebav(pol, v, ops)
+    got = co.chebav(pol["deg"], pol["mu"], pol["cc"], pol["dd"], v)
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
