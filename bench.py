@@ -256,17 +256,21 @@ def main():
             import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize()
+    tw = time.time()
     for _ in range(a.warmup):
         step_dev()
     barrier()
+    log("warm-up: %d filter applications, %.2f s each" % (a.warmup, (time.time() - tw) / max(a.warmup, 1)))
     l0 = L.nm_launch_count()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as cs:
+        torch.cuda.profiler.start()      # ncu --profile-from-start off: the launch list covers the timed region
         e0.record(stream)
         for _ in range(a.steps):
             step_dev()
         e1.record(stream)
         barrier()
+        torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     launches = int(L.nm_launch_count() - l0)
     if use_dist:
@@ -274,6 +278,7 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     ms_per_step = ms / a.steps
     value = nbytes / (ms_per_step * 1e-3) / 1e9
+    log("device-resident: %.1f ms per application, %.0f GB/s algorithmic, %d launches" % (ms_per_step, value, launches))
 
     # ---- e2e: host vectors through the C ABI
     zh = torch.empty(n, dtype=torch.float64).uniform_(-1, 1).pin_memory(); yh = torch.empty(n, dtype=torch.float64).pin_memory()

@@ -423,7 +423,7 @@ k_assemble(DevFem F) {
         if (i == j) O += FTuu_face[j];
         if (O != 0.0 || F.selfG || i == j) add_entry(F, A_, rm + i, cn + j, O);                         // :749-765
       }
-      add_entry(F, B_, rm + i, cn + i, Mmn * rhoavg * detJ);                                            // :767-779
+      if (i == 0) add_entry(F, B_, rm, cn, Mmn * rhoavg * detJ);   // :767-779; components 1,2: k_mass_replicate
     }
   }
   // ------------------------------------------------------------ fluid-solid interface face (:804-952)
@@ -451,6 +451,25 @@ k_assemble(DevFem F) {
         add_entry(F, NM_MAT_E, F.vstt[na] + i, F.pstt[nb], -mf * G.nrm[fc][i] * sj);                            // :926-948
       }
     }
+  }
+}
+
+// B = M (x) I3: the reference adds the SAME value to the three component rows of a node in the same element
+// order (:1247-1259, :767-779), so those rows are bit-identical.  The element kernel accumulates component 0
+// only; this kernel copies it to components 1 and 2 (which also keeps the three rows identical under the
+// unordered fp64 atomics, so the parcsr layer can store M once).
+__global__ void k_mass_replicate(DevMat B, int* err) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (3 * b + 2 >= B.nrow) return;
+  const int s0 = B.ia[3 * b], s1 = B.ia[3 * b + 1], s2 = B.ia[3 * b + 2], s3 = B.ia[3 * b + 3];
+  const int len = s1 - s0;
+  if (s2 - s1 != len || s3 - s2 != len) { atomicAdd(err, 1); return; }
+  for (int u = 0; u < len; ++u) {
+    const int c = B.ja[s0 + u];
+    if (B.ja[s1 + u] != c + 1 || B.ja[s2 + u] != c + 2) { atomicAdd(err, 1); return; }
+    const double v = B.val[s0 + u];
+    B.val[s1 + u] = v;
+    B.val[s2 + u] = v;
   }
 }
 
@@ -505,8 +524,17 @@ void nm_fem_assemble(NmFem& F, int job, const double* vp, const double* vs, cons
     c.launches++;
     NM_CUDA(cudaGetLastError());
   }
-  int herr[2] = {0, 0};
+  DBuf<int> d_err3(1);
+  d_err3.zero();
+  if (F.pat[NM_MAT_B].present && F.pat[NM_MAT_B].nrow > 0) {
+    NM_REQUIRE(F.pat[NM_MAT_B].nrow % 3 == 0, "assembly: B rows are not node triples");
+    k_mass_replicate<<<nm_div_up(F.pat[NM_MAT_B].nrow / 3, 128), 128, 0, c.stream>>>(D.mat[NM_MAT_B], d_err3.p);
+    c.launches++;
+  }
+  int herr[2] = {0, 0}, herr3 = 0;
   d_err.download(herr, 2);
+  d_err3.download(&herr3, 1);
+  NM_REQUIRE(herr3 == 0, "assembly: %d node triples of B do not share one column list (M (x) I3 pattern expected)", herr3);
   NM_REQUIRE(herr[0] == 0, "assembly: %d element entries have no slot in the CSR pattern (error: can not find the id)", herr[0]);
   NM_REQUIRE(herr[1] == 0, "assembly: fluid free-surface face without gravity is undefined in the reference "
                            "(src/mod_cg_create_matrix.f90:656-657); use JOB 2 for models with a fluid surface");

@@ -82,7 +82,8 @@ struct DBuf {
   void alloc(size_t n_) {
     release();
     n = n_;
-    if (n) NM_CUDA(cudaMalloc((void**)&p, n * sizeof(T)));
+    // +16 bytes: the TMA bulk copies of the streaming SpMV round slice ends up to the next 16-byte boundary
+    if (n) NM_CUDA(cudaMalloc((void**)&p, n * sizeof(T) + 16));
   }
   void release() {
     if (p) cudaFree(p);
@@ -114,6 +115,17 @@ struct NmHalo {
   DBuf<double> xg;                        // ghost values, device (gather target c >= ncol -> xg[c-ncol])
 };
 
+// Row-block plan of the streaming SpMV (nm_spmv.cuh): contiguous (block-)rows [rb0, rb0+nr) whose entries
+// [e0, e0+ne) of the format's index array fit one shared-memory stage.
+struct NmChunk { int rb0, nr_l /* nr | log2(L) << 16 */, e0, ne; };
+struct NmStreamPlan {
+  DBuf<NmChunk> chunks;
+  int nchunk = 0;                         // 0: no plan (fallback kernels)
+  int chunks_per_cta = 0, grid = 0;
+  int vcap = 0, icap = 0, rcap = 0;       // bytes of the value / index / row-pointer regions of a stage
+  int nstage = 0, smem_bytes = 0;
+};
+
 struct NmParcsr {
   int nrow_glob = 0, ncol_glob = 0;
   int nrow = 0, ncol = 0;                 // local (owned) rows / columns
@@ -128,6 +140,7 @@ struct NmParcsr {
   DBuf<int> bia, bja;
   DBuf<double> mval;
   NmHalo halo;
+  NmStreamPlan plan;
   double avg_row = 0.0;                   // mean entries per (block-)row processed by one subwarp
   long long fmt_bytes = 0;                // bytes one SpMV streams in the chosen format (matrix part)
 };

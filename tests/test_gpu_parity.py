@@ -303,3 +303,52 @@ def test_error_paths(nm):
     with pytest.raises(NmError):                                # ChebIter on an indefinite interval
         h = mv.parcsr_create(mv.COOmat([0, 2], [0, 1, 2], [0, 1], [1.0, 1.0]))
         mv.chebiter_setup(-1.0, 2.0, 5, h)
+
+
+@pytest.mark.parametrize("vbytes,maxgrid,stages", [(16384, 0, 3), (2048, 2, 2), (4096, 3, 1), (1024, 1, 4)])
+def test_streaming_kernel_ring_and_chunking(nm, monkeypatch, vbytes, maxgrid, stages):
+    """TMA-staged row-block kernel (k_stream) against the oracle product for the three formats, with stage sizes /
+    grid limits that force many chunks per CTA (ring wrap-around, mbarrier phase flips) and against the
+    global-memory fallback kernels; fused ChebIter epilogue included."""
+    from oracle import fem, solver
+    from normalmodes_b200 import matvec as mv
+    monkeypatch.setenv("NM_STREAM_VBYTES", str(vbytes))
+    monkeypatch.setenv("NM_STREAM_STAGES", str(stages))
+    if maxgrid:
+        monkeypatch.setenv("NM_STREAM_MAXGRID", str(maxgrid))
+    rng = np.random.default_rng(99)
+    for name in ("prem3k_p1_j2", "const3k_p2_j1"):
+        c = load_case(name)
+        for k, m in to_coomat(c["mats"]).items():
+            S = fem.to_scipy(c["mats"][k])
+            x = rng.uniform(-1, 1, S.shape[1])
+            monkeypatch.setenv("NM_NO_STREAM", "0")
+            h = mv.parcsr_create(m)
+            y = mv.parcsr_matvec(h, x, S.shape[0])
+            nm.nm_parcsr_free(h)
+            assert (np.abs(y - S @ x) <= _spmv_tol(S, x)).all(), (name, k)
+            monkeypatch.setenv("NM_NO_STREAM", "1")
+            h = mv.parcsr_create(m)
+            y2 = mv.parcsr_matvec(h, x, S.shape[0])
+            nm.nm_parcsr_free(h)
+            assert (np.abs(y - y2) <= 2 * _spmv_tol(S, x)).all(), (name, k)
+    # fused Chebyshev step through the streaming kernel (KRON3 B~)
+    monkeypatch.setenv("NM_NO_STREAM", "0")
+    c = load_case("const3k_p2_j1")
+    m = to_coomat(c["mats"])["B"]
+    h = mv.parcsr_create(m)
+    from normalmodes_b200._lib import check, dptr
+    d = np.empty(m.Gsiz)
+    check(nm.nm_parcsr_jacobi_scale(h, C.c_double(1.0), dptr(d)))
+    assert mv.parcsr_info(h)["format"] == "KRON3"
+    ref, _ = fem.jacobi_scale(c["mats"]["B"], 1.0)
+    St = fem.to_scipy(ref)
+    lb, ub = 0.2, 4.5
+    for deg in (1, 2, 7):
+        cheb = mv.chebiter_setup(lb, ub, deg, h)
+        b = rng.standard_normal(St.shape[0])
+        xg = mv.chebiter_solve(cheb, b)
+        xr = solver.chebiter(St, lb, ub, deg, b)
+        assert np.abs(xg - xr).max() <= 1e-13 * np.abs(xr).max()
+        nm.nm_chebiter_free(cheb)
+    nm.nm_parcsr_free(h)
