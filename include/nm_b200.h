@@ -109,6 +109,9 @@ int nm_pevsl_adopt_op(void* pevsl, void* op);
 int nm_pevsl_setbsol_chebiter(void* pevsl, void* cheb);
 int nm_pevsl_set_geneig(void* pevsl);
 int nm_pevsl_set_seed(void* pevsl, unsigned long long seed);
+/* optional, off by default (0 = pEVSL's trace test only): keep iterating until every wanted Ritz pair's Lanczos
+ * residual estimate |beta_k s_ki| is below tol (the pairs next to the band edges converge last) */
+int nm_pevsl_set_ritz_tol(void* pevsl, double tol);
 int nm_pevsl_lanbounds(void* pevsl, int mlan, int lanstep, double tol, double* lmin, double* lmax);
 int nm_pevsl_cheblannr(void* pevsl, const double* xintv4, int maxit, double tol, void* pol);
 int nm_pevsl_get_nev(void* pevsl, int* nev);

@@ -6,6 +6,49 @@
 // x += d and d = a d + b r updates in its epilogue (EpiCheb), so a step streams M once and touches
 // each vector once.
 #include "nm_spmv.cuh"
+#include <algorithm>
+
+// The iteration keeps its vectors in the PACK ORDER of a second, permuted copy of M (nm_pack_build_into): every
+// step's epilogue then reads and writes contiguous ranges and the x values a chunk gathers sit in a few
+// contiguous runs.  b is permuted in once and x out once per solve (2 of the deg+2 vector passes).
+__global__ void k_perm_gather(double* __restrict__ dst, const double* __restrict__ src, const int* __restrict__ order,
+                              int n, int R) {                    // dst[R*i+c] = src[R*order[i]+c]
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * R) return;
+  const int i = t / R;
+  dst[t] = src[R * order[i] + (t - R * i)];
+}
+__global__ void k_perm_scatter(double* __restrict__ dst, const double* __restrict__ src, const int* __restrict__ order,
+                               int n, int R) {                   // dst[R*order[i]+c] = src[R*i+c]
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * R) return;
+  const int i = t / R;
+  dst[R * order[i] + (t - R * i)] = src[t];
+}
+
+static void cheb_build_ppack(NmChebIter& C) {
+  NmParcsr& M = *C.M;
+  const char* off = getenv("NM_CHEB_PERMUTED");
+  if (M.pack.nchunk == 0 || M.format == NM_FMT_ROW3 || (off && off[0] == '0')) return;
+  const bool blk = M.format == NM_FMT_KRON3;
+  const int n = blk ? M.nbrow : M.nrow, R = blk ? 3 : 1;
+  std::vector<int> rp(n + 1), idx((size_t)(blk ? M.bja.n : M.ja.n));
+  (blk ? M.bia : M.ia).download(rp.data(), rp.size());
+  idx.resize(rp[n]);
+  (blk ? M.bja : M.ja).download(idx.data(), idx.size());
+  nm_pack_build_into(M, C.ppack, rp, idx, n, true);
+  if (C.ppack.nchunk == 0) return;
+  C.ppack_version = M.values_version;
+  C.bp.alloc(std::max(M.nrow, 1)); C.xp.alloc(std::max(M.nrow, 1));
+  if (M.halo.nsend > 0) {
+    std::vector<int> order(n), newid(n), sidx(M.halo.nsend);
+    C.ppack.order.download(order.data(), n);
+    for (int i = 0; i < n; ++i) newid[order[i]] = i;
+    M.halo.send_idx.download(sidx.data(), sidx.size());
+    for (int& v : sidx) v = R * newid[v / R] + v % R;
+    C.send_idx_p.from_host(sidx);
+  }
+}
 
 NmChebIter* nm_chebiter_build(double lb, double ub, int deg, NmParcsr* M) {
   NM_REQUIRE(M && M->nrow == M->ncol, "setup_chebiter: square matrix required");
@@ -25,13 +68,25 @@ NmChebIter* nm_chebiter_build(double lb, double ub, int deg, NmParcsr* M) {
   }
   const size_t n = M->nrow > 0 ? M->nrow : 1;
   C->r.alloc(n); C->d0.alloc(n); C->d1.alloc(n);
+  cheb_build_ppack(*C);
   return C.release();
 }
 
 void nm_chebiter_solve(NmChebIter& C, const double* b, double* x) {
   NM_REQUIRE(b != x, "chebiter: b and x must not alias");
   NmParcsr& M = *C.M;
+  NmCtx& c = nm_ctx();
   double* dbuf[2] = {C.d0.p, C.d1.p};
+  const bool perm = C.ppack.nchunk > 0;
+  const int nblk = M.format == NM_FMT_KRON3 ? M.nbrow : M.nrow, R = M.format == NM_FMT_KRON3 ? 3 : 1;
+  double* xout = x;
+  if (perm) {
+    if (C.ppack_version != M.values_version) { nm_pack_fill_from(M, C.ppack); C.ppack_version = M.values_version; }
+    k_perm_gather<<<nm_div_up(M.nrow, 256), 256, 0, c.stream>>>(C.bp.p, b, C.ppack.order.p, nblk, R);
+    c.launches++;
+    b = C.bp.p;
+    x = C.xp.p;
+  }
   const double* din = b;
   for (int k = 0; k < C.deg; ++k) {
     EpiCheb e;
@@ -42,8 +97,13 @@ void nm_chebiter_solve(NmChebIter& C, const double* b, double* x) {
     e.d_out = dbuf[k & 1];
     e.x = x;
     e.inv_theta = 1.0 / C.theta; e.ak = C.ak[k]; e.bk = C.bk[k];
-    nm_spmv_epi(M, din, e);
+    if (perm) nm_spmv_pack_epi(M, C.ppack, din, e, C.send_idx_p.p);
+    else nm_spmv_epi(M, din, e);
     din = dbuf[k & 1];
+  }
+  if (perm) {
+    k_perm_scatter<<<nm_div_up(M.nrow, 256), 256, 0, c.stream>>>(xout, C.xp.p, C.ppack.order.p, nblk, R);
+    c.launches++;
   }
   C.nsolve++;
   C.nmatvec += C.deg;

@@ -115,15 +115,25 @@ struct NmHalo {
   DBuf<double> xg;                        // ghost values, device (gather target c >= ncol -> xg[c-ncol])
 };
 
-// Row-block plan of the streaming SpMV (nm_spmv.cuh): contiguous (block-)rows [rb0, rb0+nr) whose entries
-// [e0, e0+ne) of the format's index array fit one shared-memory stage.
-struct NmChunk { int rb0, nr_l /* nr | log2(L) << 16 */, e0, ne; };
-struct NmStreamPlan {
-  DBuf<NmChunk> chunks;
-  int nchunk = 0;                         // 0: no plan (fallback kernels)
+// Packed row-block format of the streaming SpMV (nm_spmv.cuh / nm_pack.cu).  The (block-)rows are ordered for
+// locality (Cuthill-McKee on the block pattern) and cut into chunks; each chunk is ONE contiguous, 16-byte
+// aligned blob -- header, values in jagged-diagonal (JDS) order, the chunk's row ids, its DISTINCT column ids,
+// JDS column offsets, row lengths and 16-bit chunk-local column indices -- moved to shared memory by one TMA
+// bulk copy.  Vectors keep the caller's numbering: rows and columns are reached through the two id lists.
+struct NmPackDesc { unsigned off16, bytes; };   // blob offset in 16-byte units, blob size in bytes
+struct NmPackHeader { int nr, nd, ne, maxlen_L; /* maxlen | L << 16 */ };
+struct NmPack {
+  DBuf<unsigned char> blob;
+  DBuf<NmPackDesc> desc;
+  DBuf<unsigned> slot_off8;               // per value slot: position of the double in the blob (8-byte units)
+  DBuf<int> slot_src;                     // per value slot: index into the matrix' value array
+  long long nslot = 0;
+  int nchunk = 0;                         // 0: not packed (fallback kernels)
   int chunks_per_cta = 0, grid = 0;
-  int vcap = 0, icap = 0, rcap = 0;       // bytes of the value / index / row-pointer regions of a stage
-  int nstage = 0, smem_bytes = 0;
+  int stage_bytes = 0, xs_doubles = 0, nstage = 0, smem_bytes = 0;
+  long long bytes = 0;                    // blob bytes = what one product streams from HBM
+  bool permuted = false;                  // vectors in pack order (see nm_pack_build_into)
+  DBuf<int> order;                        // permuted: pack position -> caller's index row
 };
 
 struct NmParcsr {
@@ -140,7 +150,8 @@ struct NmParcsr {
   DBuf<int> bia, bja;
   DBuf<double> mval;
   NmHalo halo;
-  NmStreamPlan plan;
+  NmPack pack;
+  long long values_version = 0;           // bumped whenever the values change (dependants refill their packs)
   double avg_row = 0.0;                   // mean entries per (block-)row processed by one subwarp
   long long fmt_bytes = 0;                // bytes one SpMV streams in the chosen format (matrix part)
 };
@@ -152,6 +163,11 @@ struct NmChebIter {
   int deg = 0;
   std::vector<double> ak, bk;             // d_{k+1} = ak d_k + bk r_{k+1}
   DBuf<double> r, d0, d1;
+  // pack-order copy of M (nm_pack_build_into, permuted): the iteration runs on vectors kept in that order
+  NmPack ppack;
+  long long ppack_version = -1;
+  DBuf<double> bp, xp;                    // b and x in pack order
+  DBuf<int> send_idx_p;                   // halo send list in pack order
   long long nsolve = 0, nmatvec = 0;
   double t_total = 0;
 };
@@ -198,6 +214,7 @@ struct NmPevsl {
   double t_filter = 0, t_reorth = 0, t_total = 0, t_ritz = 0;
   long long n_filter_apply = 0;
   unsigned long long seed = 4321;
+  double ritz_tol = 0.0;                   // > 0: per-pair residual-estimate gate on top of the trace test
 };
 
 // ---------------------------------------------------------------- internal entry points
@@ -205,9 +222,16 @@ struct NmPevsl {
 NmParcsr* nm_parcsr_build(int nrow_glob, int ncol_glob, const int* row_starts, const int* col_starts,
                           const int* ia, const int* ja, const double* a);
 NmParcsr* nm_parcsr_scaled_copy(const NmParcsr& M, const double* drow_dev, const double* dcol_dev);
-void nm_halo_exchange(NmParcsr& M, const double* x);
+void nm_halo_exchange(NmParcsr& M, const double* x, const int* send_idx = nullptr);   // send_idx: override of the pack list
 void nm_spmv(NmParcsr& M, const double* x, double* y);                 // y = M x   (device pointers)
 void nm_spmv_add(NmParcsr& M, const double* x, double* y);             // y += M x
+// packed format (nm_pack.cu): rp/idx = host row pointers and column ids of the chosen format, n (block-)rows
+void nm_pack_build(NmParcsr& M, const std::vector<int>& rp, const std::vector<int>& idx, int n);
+void nm_pack_build_into(NmParcsr& M, NmPack& P, const std::vector<int>& rp, const std::vector<int>& idx, int n,
+                        bool permuted);
+void nm_pack_fill(NmParcsr& M);                                        // (re)load the blob values from M.mval / M.a
+void nm_pack_fill_from(NmParcsr& M, NmPack& P);
+void nm_pack_clone(const NmParcsr& src, NmParcsr& dst);                // same structure, values from dst
 // chebiter
 NmChebIter* nm_chebiter_build(double lb, double ub, int deg, NmParcsr* M);
 void nm_chebiter_solve(NmChebIter& C, const double* b, double* x);

@@ -361,7 +361,17 @@ void nm_cheblannr(NmPevsl& P, const double xintv[4], int maxit, double tol, cons
     double tr1 = 0.0;
     for (int i = 0; i < kdim; ++i)
       if (th[i] + DBL_EPS_MULT * 2.220446049250313e-16 >= bar) tr1 += th[i];
-    if (fabs(tr1 - tr0) < tol * fabs(tr1)) break;
+    bool done = fabs(tr1 - tr0) < tol * fabs(tr1);
+    if (done && P.ritz_tol > 0.0) {
+      // optional gate on top of pEVSL's trace test: every wanted Ritz pair's Lanczos residual estimate
+      // |beta_k s_ki| must be below ritz_tol (the pairs next to the band edges converge last)
+      std::vector<double> lastrow(kdim);
+      rc = nm_tridiag_eig_ex(kdim, dT.data(), eT.data(), th.data(), nullptr, lastrow.data());
+      NM_REQUIRE(rc == 0, "cheblannr: tridiagonal eigensolver failed");
+      for (int i = 0; i < kdim; ++i)
+        if (th[i] >= bar && fabs(beta * lastrow[i]) > P.ritz_tol) { done = false; break; }
+    }
+    if (done) break;
     tr0 = tr1;
   }
   for (auto& e : ev) cudaEventDestroy(e);
@@ -411,6 +421,11 @@ void nm_cheblannr(NmPevsl& P, const double xintv[4], int maxit, double tol, cons
 }
 
 // ---------------------------------------------------------------- C ABI: solver context
+extern "C" int nm_pevsl_set_ritz_tol(void* h, double tol) {
+  NM_API_BEGIN
+  ((NmPevsl*)h)->ritz_tol = tol;
+  NM_API_END
+}
 extern "C" int nm_pevsl_create(void** out) {
   NM_API_BEGIN
   nm_ensure_init();

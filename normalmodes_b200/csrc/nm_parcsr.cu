@@ -11,12 +11,12 @@ __global__ void k_pack(double* __restrict__ buf, const double* __restrict__ x, c
   if (i < n) buf[i] = x[idx[i]];
 }
 
-void nm_halo_exchange(NmParcsr& M, const double* x) {
+void nm_halo_exchange(NmParcsr& M, const double* x, const int* send_idx) {
   NmCtx& c = nm_ctx();
   NmHalo& h = M.halo;
   if (c.nranks == 1 || (h.nghost == 0 && h.nsend == 0)) return;
   if (h.nsend > 0) {
-    k_pack<<<nm_div_up(h.nsend, 256), 256, 0, c.stream>>>(h.sendbuf.p, x, h.send_idx.p, h.nsend);
+    k_pack<<<nm_div_up(h.nsend, 256), 256, 0, c.stream>>>(h.sendbuf.p, x, send_idx ? send_idx : h.send_idx.p, h.nsend);
     c.launches++;
   }
   NM_NCCL(ncclGroupStart());
@@ -123,67 +123,6 @@ static bool detect_kron3(int nrow, const std::vector<int>& ia, const std::vector
   return true;
 }
 
-// ---------------------------------------------------------------- row-block plan of the streaming kernel
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return (v && v[0]) ? atoi(v) : dflt;
-}
-// rp: host row pointers of the chosen format (bia for ROW3/KRON3, ia for CSR), n (block-)rows.
-static void build_stream_plan(NmParcsr& M, const std::vector<int>& rp, int n) {
-  NmStreamPlan& P = M.plan;
-  P.nchunk = 0;
-  if (n == 0 || env_int("NM_NO_STREAM", 0)) return;
-  const int fmt = M.format;
-  const int vpe = fmt == NM_FMT_ROW3 ? 9 : 1;
-  const int rows_per = fmt == NM_FMT_CSR ? 1 : 3;
-  const int rcap_rows = NM_SPMV_THREADS / rows_per;                         // one epilogue thread per scalar row
-  const int vbytes_cap = env_int("NM_STREAM_VBYTES", fmt == NM_FMT_ROW3 ? 24576 : 12288);
-  const int ecap = vbytes_cap / (8 * vpe);
-  std::vector<NmChunk> ch;
-  int r = 0;
-  int maxe = 0, maxr = 0;
-  while (r < n) {
-    NmChunk c;
-    c.rb0 = r; c.e0 = rp[r];
-    int e = 0, k = 0;
-    while (r + k < n && k < rcap_rows) {
-      const int len = rp[r + k + 1] - rp[r + k];
-      if (e + len > ecap) break;
-      e += len; ++k;
-    }
-    if (k == 0) return;                                                     // a single row exceeds a stage: fallback
-    int logL = 0;                                                           // lanes per scalar row: fill the CTA
-    while (logL < 5 && rows_per * k * (2 << logL) <= NM_SPMV_THREADS) ++logL;
-    c.nr_l = k | (logL << 16); c.ne = e;
-    ch.push_back(c);
-    maxe = std::max(maxe, e); maxr = std::max(maxr, k);
-    r += k;
-  }
-  P.vcap = ((maxe * vpe * 8 + 16) + 15) & ~15;
-  P.icap = ((maxe * 4 + 16) + 15) & ~15;
-  P.rcap = (((maxr + 1) * 4 + 16) + 15) & ~15;
-  P.nstage = std::max(1, std::min(8, env_int("NM_STREAM_STAGES", 2)));
-  const int fixed = NM_STREAM_MAXDESC * (int)sizeof(NmChunk) + 64;
-  P.smem_bytes = fixed + P.nstage * (P.vcap + P.icap + P.rcap);
-  if (P.smem_bytes > 200 * 1024) return;
-  P.nchunk = (int)ch.size();
-  int ctas = nm_ctx().sm_count * std::max(1, env_int("NM_STREAM_CTAS_PER_SM", 4));
-  ctas = std::max(1, std::min(ctas, env_int("NM_STREAM_MAXGRID", ctas)));     // tests: force several chunks per CTA
-  P.grid = std::min(P.nchunk, ctas);
-  P.chunks_per_cta = nm_div_up(P.nchunk, P.grid);
-  if (P.chunks_per_cta > NM_STREAM_MAXDESC) P.chunks_per_cta = NM_STREAM_MAXDESC;
-  P.grid = nm_div_up(P.nchunk, P.chunks_per_cta);
-  P.chunks.from_host(ch);
-}
-static void clone_stream_plan(const NmStreamPlan& src, NmStreamPlan& dst) {
-  dst.nchunk = src.nchunk; dst.chunks_per_cta = src.chunks_per_cta; dst.grid = src.grid;
-  dst.vcap = src.vcap; dst.icap = src.icap; dst.rcap = src.rcap; dst.nstage = src.nstage; dst.smem_bytes = src.smem_bytes;
-  if (src.nchunk > 0) {
-    dst.chunks.alloc(src.chunks.n);
-    NM_CUDA(cudaMemcpyAsync(dst.chunks.p, src.chunks.p, src.chunks.n * sizeof(NmChunk), cudaMemcpyDeviceToDevice, nm_ctx().stream));
-  }
-}
-
 static void choose_format(NmParcsr& M, const std::vector<int>& ia, const std::vector<int>& ja, const double* a) {
   std::vector<int> bia, bja;
   std::vector<double> mval;
@@ -192,23 +131,23 @@ static void choose_format(NmParcsr& M, const std::vector<int>& ia, const std::ve
   M.format = NM_FMT_CSR;
   M.avg_row = M.nrow ? (double)M.nnz / M.nrow : 0.0;
   M.fmt_bytes = 12ll * M.nnz + 4ll * (M.nrow + 1);
-  if (force && force[0] == '1') { build_stream_plan(M, ia, M.nrow); return; }
+  if (force && force[0] == '1') { nm_pack_build(M, ia, ja, M.nrow); return; }
   if (aligned && M.nnz > 0 && detect_kron3(M.nrow, ia, ja, a, bia, bja, mval)) {
     M.format = NM_FMT_KRON3;
     M.nbrow = M.nrow / 3;
     M.bia.from_host(bia); M.bja.from_host(bja); M.mval.from_host(mval);
     M.avg_row = (double)bja.size() / M.nbrow;
     M.fmt_bytes = 12ll * (long long)bja.size() + 4ll * (M.nbrow + 1);
-    build_stream_plan(M, bia, M.nbrow);
+    nm_pack_build(M, bia, bja, M.nbrow);
   } else if (aligned && M.nnz > 0 && detect_row3(M.nrow, ia, ja, bia, bja)) {
     M.format = NM_FMT_ROW3;
     M.nbrow = M.nrow / 3;
     M.bia.from_host(bia); M.bja.from_host(bja);
     M.avg_row = 3.0 * (double)bja.size() / M.nbrow;
     M.fmt_bytes = 8ll * M.nnz + 4ll * (long long)bja.size() + 4ll * (M.nbrow + 1);
-    build_stream_plan(M, bia, M.nbrow);
+    nm_pack_build(M, bia, bja, M.nbrow);
   } else {
-    build_stream_plan(M, ia, M.nrow);
+    nm_pack_build(M, ia, ja, M.nrow);
   }
 }
 
@@ -286,13 +225,6 @@ NmParcsr* nm_parcsr_scaled_copy(const NmParcsr& M, const double* dr, const doubl
   if (S->format == NM_FMT_ROW3) { clone_i(M.bia, S->bia); clone_i(M.bja, S->bja); }
   if (S->format == NM_FMT_CSR) { S->avg_row = M.nrow ? (double)M.nnz / M.nrow : 0; S->fmt_bytes = 12ll * M.nnz + 4ll * (M.nrow + 1); }
   S->a.alloc(std::max<size_t>((size_t)M.nnz, 1));
-  if (S->format == M.format) {
-    clone_stream_plan(M.plan, S->plan);
-  } else {                                                    // KRON3 source -> CSR copy: plan over the scalar rows
-    std::vector<int> hia(M.nrow + 1);
-    M.ia.download(hia.data(), hia.size());
-    build_stream_plan(*S, hia, S->nrow);
-  }
   // halo plan is shared by value (index lists cloned)
   S->halo.nghost = M.halo.nghost; S->halo.ghost_glob = M.halo.ghost_glob;
   S->halo.recv_cnt = M.halo.recv_cnt; S->halo.recv_off = M.halo.recv_off;
@@ -306,6 +238,14 @@ NmParcsr* nm_parcsr_scaled_copy(const NmParcsr& M, const double* dr, const doubl
     k_scale_csr<<<nm_div_up(M.nrow, 128), 128, 0, c.stream>>>(M.nrow, M.ncol, M.ia.p, M.ja.p, M.a.p, S->a.p, dr, dc,
                                                               S->halo.xg.p);
     c.launches++;
+  }
+  if (S->format == M.format) {
+    nm_pack_clone(M, *S);
+  } else {                                                    // KRON3 source -> CSR copy: pack the scalar rows
+    std::vector<int> hia(M.nrow + 1), hja((size_t)M.nnz);
+    M.ia.download(hia.data(), hia.size());
+    M.ja.download(hja.data(), hja.size());
+    nm_pack_build(*S, hia, hja, S->nrow);
   }
   NM_CUDA(cudaStreamSynchronize(c.stream));
   return S.release();
@@ -370,6 +310,7 @@ extern "C" int nm_parcsr_jacobi_scale(void* h, double sign, double* d_host) {
       k_kron_refresh<<<nm_div_up(M.nbrow, 128), 128, 0, c.stream>>>(M.nbrow, M.bia.p, M.ia.p, M.a.p, M.mval.p);
       c.launches++;
     }
+    nm_pack_fill(M);
   }
   if (d_host) d.download(d_host, n);
   NM_CUDA(cudaStreamSynchronize(c.stream));

@@ -44,7 +44,7 @@ class Result:
     pass
 
 
-def pnm_apply_pevsl(mv, lowfreq, upfreq, log=None, maxit=None, tol=1.0e-5, seed=None, recheck=True):
+def pnm_apply_pevsl(mv, lowfreq, upfreq, log=None, maxit=None, tol=1.0e-5, seed=None, recheck=True, ritz_tol=None):
     """src/mod_pevsl.f90:16-222 (without the MPI-IO writers).  mv: matvec.MatVec from setupmatvec."""
     L = lib()
     t0 = time.time()
@@ -52,6 +52,8 @@ def pnm_apply_pevsl(mv, lowfreq, upfreq, log=None, maxit=None, tol=1.0e-5, seed=
     pevslAB = mvmod.Pevsl(mv.Gpbsiz, mv.pbsiz, mv.nfirst)                      # :54-57
     if seed is not None:
         check(L.nm_pevsl_set_seed(pevslAB.h, C.c_ulonglong(seed)))
+    if ritz_tol is not None:
+        check(L.nm_pevsl_set_ritz_tol(pevslAB.h, C.c_double(ritz_tol)))
     pevslAB.setbmv_op(mv.opB)                                                   # PEVSL_SETBMV_F90(sparseBV) :69
     pevslAB.setbsol_chebiter(mv.chebB)                                          # CHEBTYPE = 2 :72-73
     pevslAB.setamv_op(mv.opA)                                                   # sparseAV | sparsefsAV :76-80

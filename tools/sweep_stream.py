@@ -20,9 +20,10 @@ def main():
     p.add_argument("--porder", type=int, default=2)
     p.add_argument("--job", type=int, default=2)
     p.add_argument("--which", default="B,Ad,Ap")
-    p.add_argument("--vbytes", default="8192,12288,16384,24576")
+    p.add_argument("--entries", default="1024,1536,2048")
+    p.add_argument("--distinct", default="768")
     p.add_argument("--stages", default="2,3")
-    p.add_argument("--ctas", default="2,3,4")
+    p.add_argument("--ctas", default="3,4,5")
     p.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep_stream.json"))
     a = p.parse_args()
     import torch
@@ -43,17 +44,19 @@ def main():
         nrow = m.siz(0); ncol = int(m.coldist[1] - m.coldist[0])
         z = torch.empty(max(nrow, ncol), dtype=torch.float64, device="cuda").uniform_(-1, 1)
         y = torch.empty_like(z)
-        combos = [(None, None, None)] + list(itertools.product([int(v) for v in a.vbytes.split(",")],
-                                                               [int(v) for v in a.stages.split(",")],
-                                                               [int(v) for v in a.ctas.split(",")]))
-        for vb, st, ct in combos:
+        combos = [(None, None, None, None)] + list(itertools.product([int(v) for v in a.entries.split(",")],
+                                                                     [int(v) for v in a.distinct.split(",")],
+                                                                     [int(v) for v in a.stages.split(",")],
+                                                                     [int(v) for v in a.ctas.split(",")]))
+        for vb, dc, st, ct in combos:
             if vb is None:
-                os.environ["NM_NO_STREAM"] = "1"
+                os.environ["NM_NO_PACK"] = "1"
             else:
-                os.environ["NM_NO_STREAM"] = "0"
-                os.environ["NM_STREAM_VBYTES"] = str(vb * (2 if which in ("Ad", "A") else 1))
-                os.environ["NM_STREAM_STAGES"] = str(st)
-                os.environ["NM_STREAM_CTAS_PER_SM"] = str(ct)
+                os.environ["NM_NO_PACK"] = "0"
+                os.environ["NM_PACK_ENTRIES"] = str(vb // 6 if which in ("Ad", "A") else vb)
+                os.environ["NM_PACK_DISTINCT"] = str(dc // 3 if which in ("Ad", "A") else dc)
+                os.environ["NM_PACK_STAGES"] = str(st)
+                os.environ["NM_PACK_CTAS_PER_SM"] = str(ct)
             h = mvmod.parcsr_create(m)
             info = mvmod.parcsr_info(h)
             cheb = None
@@ -77,7 +80,7 @@ def main():
             e1.record(stream)
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / (reps * per)
-            r = dict(which=which, format=info["format"], vbytes=vb, stages=st, ctas=ct, us=us, format_gbs=nbytes / us / 1e3)
+            r = dict(which=which, format=info["format"], entries=vb, distinct=dc, stages=st, ctas=ct, us=us, fmt_bytes=info["fmt_bytes"], format_gbs=nbytes / us / 1e3)
             res.append(r)
             bench.log(json.dumps(r))
             if cheb is not None:
