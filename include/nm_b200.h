@@ -55,6 +55,8 @@ int nm_chebiter_free(void* cheb);
 int nm_chebiter_solve_host(void* cheb, const double* b, double* x);
 int nm_chebiter_solve_dev(void* cheb, const double* b_dev, double* x_dev);
 int nm_chebiter_stats(void* cheb, long long* nsolve, long long* nmatvec, int* deg, double* lmin, double* lmax);
+/* kind: 0 plain kernels, 1 TMA-staged packed kernel, 2 sliced JDS; bytes: matrix bytes one step streams */
+int nm_chebiter_pack_info(void* cheb, int* kind, long long* bytes);
 
 /* ---- operators: the callbacks sparseAV / sparsefsAV / sparseBV / sparseApV (mod_matvec.f90:445-520) ---- */
 int nm_op_create_csr(void* mat, void** op_out);                               /* w = M v                        */

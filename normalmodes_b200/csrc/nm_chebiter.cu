@@ -29,20 +29,28 @@ __global__ void k_perm_scatter(double* __restrict__ dst, const double* __restric
 static void cheb_build_ppack(NmChebIter& C) {
   NmParcsr& M = *C.M;
   const char* off = getenv("NM_CHEB_PERMUTED");
-  if (M.pack.nchunk == 0 || M.format == NM_FMT_ROW3 || (off && off[0] == '0')) return;
+  if (M.format == NM_FMT_ROW3 || M.nrow == 0 || (off && off[0] == '0')) return;
   const bool blk = M.format == NM_FMT_KRON3;
   const int n = blk ? M.nbrow : M.nrow, R = blk ? 3 : 1;
   std::vector<int> rp(n + 1), idx((size_t)(blk ? M.bja.n : M.ja.n));
   (blk ? M.bia : M.ia).download(rp.data(), rp.size());
   idx.resize(rp[n]);
   (blk ? M.bja : M.ja).download(idx.data(), idx.size());
-  nm_pack_build_into(M, C.ppack, rp, idx, n, true);
-  if (C.ppack.nchunk == 0) return;
+  const int* order_dev = nullptr;
+  if (nm_use_sell()) {
+    nm_sell_build_into(M, C.psell, rp, idx, n, true);
+    if (C.psell.nchunk == 0) return;
+    order_dev = C.psell.order.p;
+  } else {
+    nm_pack_build_into(M, C.ppack, rp, idx, n, true);
+    if (C.ppack.nchunk == 0) return;
+    order_dev = C.ppack.order.p;
+  }
   C.ppack_version = M.values_version;
   C.bp.alloc(std::max(M.nrow, 1)); C.xp.alloc(std::max(M.nrow, 1));
   if (M.halo.nsend > 0) {
     std::vector<int> order(n), newid(n), sidx(M.halo.nsend);
-    C.ppack.order.download(order.data(), n);
+    NM_CUDA(cudaMemcpy(order.data(), order_dev, n * sizeof(int), cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; ++i) newid[order[i]] = i;
     M.halo.send_idx.download(sidx.data(), sidx.size());
     for (int& v : sidx) v = R * newid[v / R] + v % R;
@@ -77,12 +85,16 @@ void nm_chebiter_solve(NmChebIter& C, const double* b, double* x) {
   NmParcsr& M = *C.M;
   NmCtx& c = nm_ctx();
   double* dbuf[2] = {C.d0.p, C.d1.p};
-  const bool perm = C.ppack.nchunk > 0;
+  const bool perm = C.ppack.nchunk > 0 || C.psell.nchunk > 0;
+  const int* order_dev = C.psell.nchunk > 0 ? C.psell.order.p : C.ppack.order.p;
   const int nblk = M.format == NM_FMT_KRON3 ? M.nbrow : M.nrow, R = M.format == NM_FMT_KRON3 ? 3 : 1;
   double* xout = x;
   if (perm) {
-    if (C.ppack_version != M.values_version) { nm_pack_fill_from(M, C.ppack); C.ppack_version = M.values_version; }
-    k_perm_gather<<<nm_div_up(M.nrow, 256), 256, 0, c.stream>>>(C.bp.p, b, C.ppack.order.p, nblk, R);
+    if (C.ppack_version != M.values_version) {
+      nm_pack_fill_from(M, C.ppack); nm_sell_fill_from(M, C.psell);
+      C.ppack_version = M.values_version;
+    }
+    k_perm_gather<<<nm_div_up(M.nrow, 256), 256, 0, c.stream>>>(C.bp.p, b, order_dev, nblk, R);
     c.launches++;
     b = C.bp.p;
     x = C.xp.p;
@@ -97,12 +109,13 @@ void nm_chebiter_solve(NmChebIter& C, const double* b, double* x) {
     e.d_out = dbuf[k & 1];
     e.x = x;
     e.inv_theta = 1.0 / C.theta; e.ak = C.ak[k]; e.bk = C.bk[k];
-    if (perm) nm_spmv_pack_epi(M, C.ppack, din, e, C.send_idx_p.p);
+    if (C.psell.nchunk > 0) nm_spmv_sell_epi(M, C.psell, din, e, C.send_idx_p.p);
+    else if (perm) nm_spmv_pack_epi(M, C.ppack, din, e, C.send_idx_p.p);
     else nm_spmv_epi(M, din, e);
     din = dbuf[k & 1];
   }
   if (perm) {
-    k_perm_scatter<<<nm_div_up(M.nrow, 256), 256, 0, c.stream>>>(xout, C.xp.p, C.ppack.order.p, nblk, R);
+    k_perm_scatter<<<nm_div_up(M.nrow, 256), 256, 0, c.stream>>>(xout, C.xp.p, order_dev, nblk, R);
     c.launches++;
   }
   C.nsolve++;
@@ -136,6 +149,16 @@ extern "C" int nm_chebiter_solve_host(void* h, const double* b, double* x) {
 extern "C" int nm_chebiter_solve_dev(void* h, const double* b_dev, double* x_dev) {
   NM_API_BEGIN
   nm_chebiter_solve(*(NmChebIter*)h, b_dev, x_dev);
+  NM_API_END
+}
+// kind: 0 = plain kernels on the caller's numbering, 1 = TMA-staged packed kernel (k_pack), 2 = sliced JDS (k_sell),
+// both on vectors kept in pack order; bytes = matrix bytes one iteration step streams
+extern "C" int nm_chebiter_pack_info(void* h, int* kind, long long* bytes) {
+  NM_API_BEGIN
+  NmChebIter& C = *(NmChebIter*)h;
+  const int k = C.psell.nchunk > 0 ? 2 : (C.ppack.nchunk > 0 ? 1 : 0);
+  if (kind) *kind = k;
+  if (bytes) *bytes = k == 2 ? C.psell.bytes : (k == 1 ? C.ppack.bytes : C.M->fmt_bytes);
   NM_API_END
 }
 extern "C" int nm_chebiter_stats(void* h, long long* nsolve, long long* nmatvec, int* deg, double* lmin, double* lmax) {

@@ -136,6 +136,24 @@ struct NmPack {
   DBuf<int> order;                        // permuted: pack position -> caller's index row
 };
 
+// Sliced JDS format read straight from global memory (k_sell, nm_spmv.cuh): the locality/length-class row order
+// of nm_pack.cu cut into slices of 256/(R*L) rows of one length class; inside a slice rows are sorted by length
+// and entry k of the j-th longest row sits at e0 + off[k] + j, so the lanes of a warp (neighbouring rows) read
+// neighbouring values / column ids (coalesced) with no padding.  One thread block per slice, L lanes per row.
+struct NmSellChunk { long long e0; int o0, r0, nr, L, maxlen, pad; };
+struct NmSell {
+  DBuf<double> val;                       // VPE values per entry, JDS order
+  DBuf<int> col;                          // (block-)column id per entry (in the vectors' numbering)
+  DBuf<int> off, rows, rowlen;            // JDS column offsets per slice; row ids; row lengths
+  DBuf<NmSellChunk> chunks;
+  DBuf<int> slot_src;                     // per value slot: index into the matrix' value array
+  long long nslot = 0;
+  int nchunk = 0;                         // 0: not built
+  long long bytes = 0;                    // bytes one product streams
+  bool permuted = false;                  // vectors in slice order
+  DBuf<int> order;                        // permuted: position -> caller's index row
+};
+
 struct NmParcsr {
   int nrow_glob = 0, ncol_glob = 0;
   int nrow = 0, ncol = 0;                 // local (owned) rows / columns
@@ -151,6 +169,7 @@ struct NmParcsr {
   DBuf<double> mval;
   NmHalo halo;
   NmPack pack;
+  NmSell sell;
   long long values_version = 0;           // bumped whenever the values change (dependants refill their packs)
   double avg_row = 0.0;                   // mean entries per (block-)row processed by one subwarp
   long long fmt_bytes = 0;                // bytes one SpMV streams in the chosen format (matrix part)
@@ -165,6 +184,7 @@ struct NmChebIter {
   DBuf<double> r, d0, d1;
   // pack-order copy of M (nm_pack_build_into, permuted): the iteration runs on vectors kept in that order
   NmPack ppack;
+  NmSell psell;
   long long ppack_version = -1;
   DBuf<double> bp, xp;                    // b and x in pack order
   DBuf<int> send_idx_p;                   // halo send list in pack order
@@ -231,6 +251,11 @@ void nm_pack_build_into(NmParcsr& M, NmPack& P, const std::vector<int>& rp, cons
                         bool permuted);
 void nm_pack_fill(NmParcsr& M);                                        // (re)load the blob values from M.mval / M.a
 void nm_pack_fill_from(NmParcsr& M, NmPack& P);
+void nm_sell_build_into(NmParcsr& M, NmSell& S, const std::vector<int>& rp, const std::vector<int>& idx, int n,
+                        bool permuted);
+void nm_sell_fill_from(NmParcsr& M, NmSell& S);
+void nm_sell_clone(const NmParcsr& src, NmParcsr& dst);
+bool nm_use_sell();                                                    // NM_KERNEL_SELL (default 1): k_sell instead of k_pack
 void nm_pack_clone(const NmParcsr& src, NmParcsr& dst);                // same structure, values from dst
 // chebiter
 NmChebIter* nm_chebiter_build(double lb, double ub, int deg, NmParcsr* M);

@@ -54,9 +54,21 @@ static void cm_order(int n, const std::vector<int>& rp, const std::vector<int>& 
   }
 }
 
+bool nm_use_sell() { return env_int_("NM_KERNEL_SELL", 0) != 0; }
+
 static inline size_t up16(size_t v) { return (v + 15) & ~(size_t)15; }
 
+// Pack of a matrix whose vectors stay in the caller's numbering.  Off by default: measured on B200 (tools/
+// sweep_stream.py, profiles/) the plain global-memory kernels are as fast for one-off products in natural order
+// (ROW3 A: 135 us vs 144-244 us; E / ET within 10%); the packed kernels pay off where the vectors can live in
+// pack order, i.e. inside the Chebyshev iterations (NmChebIter builds its own permuted pack).
 void nm_pack_build(NmParcsr& M, const std::vector<int>& rp, const std::vector<int>& idx, int n) {
+  if (!env_int_("NM_NATURAL_PACK", 0)) return;
+  if (nm_use_sell()) {
+    nm_sell_build_into(M, M.sell, rp, idx, n, false);
+    if (M.sell.nchunk > 0) M.fmt_bytes = M.sell.bytes;
+    return;
+  }
   nm_pack_build_into(M, M.pack, rp, idx, n, false);
   if (M.pack.nchunk > 0) M.fmt_bytes = M.pack.bytes;
 }
@@ -74,7 +86,7 @@ void nm_pack_build_into(NmParcsr& M, NmPack& P, const std::vector<int>& rp, cons
   const int fmt = M.format;
   const int R = fmt == NM_FMT_CSR ? 1 : 3;
   const int VPE = fmt == NM_FMT_ROW3 ? 9 : 1;
-  const int ecap = std::max(32, env_int_("NM_PACK_ENTRIES", fmt == NM_FMT_ROW3 ? 192 : 1024));
+  const int ecap = std::max(32, env_int_("NM_PACK_ENTRIES", fmt == NM_FMT_ROW3 ? 192 : 1536));
   const int rcap = std::min(NM_SPMV_THREADS / R, std::max(1, env_int_("NM_PACK_ROWS", NM_SPMV_THREADS)));
   const int dcap = std::max(16, std::min(4096, env_int_("NM_PACK_DISTINCT", fmt == NM_FMT_ROW3 ? 160 : 448)));
   const int ncolb = (M.ncol + M.halo.nghost + R - 1) / R;                   // column ids are < ncolb
@@ -252,7 +264,7 @@ void nm_pack_build_into(NmParcsr& M, NmPack& P, const std::vector<int>& rp, cons
   // ---- 4. launch geometry
   P.xs_doubles = R * max_nd;
   P.stage_bytes = (int)up16(max_blob);
-  P.nstage = std::max(2, std::min(8, env_int_("NM_PACK_STAGES", 3)));
+  P.nstage = std::max(2, std::min(8, env_int_("NM_PACK_STAGES", 2)));
   const int fixed = NM_PACK_MAXDESC * (int)sizeof(NmPackDesc) + 64 + 16 * P.xs_doubles + 16 * 3 * NM_SPMV_THREADS;
   P.smem_bytes = (int)up16(fixed) + P.nstage * P.stage_bytes;
   if (P.smem_bytes > 200 * 1024) return;
@@ -284,6 +296,7 @@ __global__ void k_pack_fill(long long nslot, const unsigned* __restrict__ off8, 
 void nm_pack_fill(NmParcsr& M) {
   M.values_version++;
   nm_pack_fill_from(M, M.pack);
+  nm_sell_fill_from(M, M.sell);
 }
 
 void nm_pack_fill_from(NmParcsr& M, NmPack& P) {
@@ -295,6 +308,8 @@ void nm_pack_fill_from(NmParcsr& M, NmPack& P) {
 }
 
 void nm_pack_clone(const NmParcsr& src, NmParcsr& dst) {
+  nm_sell_clone(src, dst);
+  if (dst.sell.nchunk > 0) dst.fmt_bytes = dst.sell.bytes;
   const NmPack& S = src.pack;
   NmPack& D = dst.pack;
   D.nchunk = 0;
@@ -310,4 +325,118 @@ void nm_pack_clone(const NmParcsr& src, NmParcsr& dst) {
   D.nchunk = S.nchunk;
   dst.fmt_bytes = D.bytes;
   nm_pack_fill_from(dst, D);
+}
+
+// ================================================================ sliced JDS (k_sell)
+void nm_sell_build_into(NmParcsr& M, NmSell& S, const std::vector<int>& rp, const std::vector<int>& idx, int n,
+                        bool permuted) {
+  S.nchunk = 0;
+  S.permuted = false;
+  if (n == 0 || env_int_("NM_NO_SELL", 0)) return;
+  if (permuted && M.nrow != M.ncol) return;
+  const int fmt = M.format;
+  const int R = fmt == NM_FMT_CSR ? 1 : 3;
+  const int VPE = fmt == NM_FMT_ROW3 ? 9 : 1;
+  const int target = std::max(1, env_int_("NM_SELL_TARGET", fmt == NM_FMT_ROW3 ? 12 : 24));   // entries per lane
+  std::vector<int> order;
+  if (M.nrow == M.ncol && env_int_("NM_PACK_ORDER", 1)) cm_order(n, rp, idx, order);
+  else { order.resize(n); std::iota(order.begin(), order.end(), 0); }
+  auto cls = [&](int row) { int len = rp[row + 1] - rp[row], c = 0; while ((1 << c) <= len) ++c; return c; };
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cls(a) < cls(b); });
+  // ---- slices: rows of one length class, L lanes per row
+  std::vector<NmSellChunk> chunks;
+  std::vector<int> final_order(n);
+  long long e0 = 0;
+  int o0 = 0;
+  for (int r = 0; r < n;) {
+    const int c0 = cls(order[r]);
+    const int len0 = rp[order[r] + 1] - rp[order[r]];
+    int L = 1;
+    while (L < 32 && len0 >= 2 * L * target) L *= 2;
+    const int cap = std::max(1, NM_SPMV_THREADS / (R * L));
+    int k = 0;
+    while (r + k < n && k < cap && cls(order[r + k]) == c0) ++k;
+    std::copy(order.begin() + r, order.begin() + r + k, final_order.begin() + r);
+    std::stable_sort(final_order.begin() + r, final_order.begin() + r + k,
+                     [&](int a, int b) { return rp[a + 1] - rp[a] > rp[b + 1] - rp[b]; });
+    NmSellChunk c;
+    c.e0 = e0; c.o0 = o0; c.r0 = r; c.nr = k; c.L = L; c.pad = 0;
+    c.maxlen = rp[final_order[r] + 1] - rp[final_order[r]];
+    long long ne = 0;
+    for (int j = 0; j < k; ++j) ne += rp[final_order[r + j] + 1] - rp[final_order[r + j]];
+    e0 += ne; o0 += c.maxlen + 1;
+    chunks.push_back(c);
+    r += k;
+  }
+  NM_REQUIRE(e0 == rp[n], "sell: entry count mismatch");
+  std::vector<int> newid;
+  if (permuted) {
+    newid.resize(n);
+    for (int i = 0; i < n; ++i) newid[final_order[i]] = i;
+  }
+  auto colid = [&](int c) { return (permuted && c < n) ? newid[c] : c; };
+  std::vector<int> col((size_t)e0), off((size_t)o0), rows(n), rowlen(n), src((size_t)e0 * VPE);
+  for (const NmSellChunk& c : chunks) {
+    int pos = 0;
+    for (int k = 0; k <= c.maxlen; ++k) {
+      off[c.o0 + k] = pos;
+      int cnt = 0;
+      while (cnt < c.nr && rp[final_order[c.r0 + cnt] + 1] - rp[final_order[c.r0 + cnt]] > k) ++cnt;
+      pos += cnt;
+    }
+    for (int j = 0; j < c.nr; ++j) {
+      const int row = final_order[c.r0 + j];
+      const int s = rp[row], len = rp[row + 1] - s;
+      rows[c.r0 + j] = permuted ? c.r0 + j : row;
+      rowlen[c.r0 + j] = len;
+      for (int k = 0; k < len; ++k) {
+        const long long p = c.e0 + off[c.o0 + k] + j;
+        col[p] = colid(idx[s + k]);
+        if (VPE == 1) src[p] = s + k;
+        else
+          for (int pi = 0; pi < 3; ++pi)
+            for (int cc = 0; cc < 3; ++cc) src[p * 9 + pi * 3 + cc] = 9 * s + pi * 3 * len + 3 * k + cc;
+      }
+    }
+  }
+  S.val.alloc((size_t)e0 * VPE);
+  S.col.from_host(col); S.off.from_host(off); S.rows.from_host(rows); S.rowlen.from_host(rowlen);
+  S.chunks.from_host(chunks); S.slot_src.from_host(src);
+  S.nslot = (long long)src.size();
+  S.bytes = (long long)e0 * (8 * VPE + 4) + 4ll * o0 + 8ll * n + (long long)chunks.size() * sizeof(NmSellChunk);
+  S.nchunk = (int)chunks.size();
+  S.permuted = permuted;
+  if (permuted) S.order.from_host(final_order);
+  nm_sell_fill_from(M, S);
+}
+
+__global__ void k_sell_fill(long long nslot, const int* __restrict__ src, const double* __restrict__ vals,
+                            double* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < nslot) out[i] = vals[src[i]];
+}
+
+void nm_sell_fill_from(NmParcsr& M, NmSell& S) {
+  if (S.nchunk == 0 || S.nslot == 0) return;
+  NmCtx& c = nm_ctx();
+  const double* vals = M.format == NM_FMT_KRON3 ? M.mval.p : M.a.p;
+  k_sell_fill<<<nm_div_up(S.nslot, 256), 256, 0, c.stream>>>(S.nslot, S.slot_src.p, vals, S.val.p);
+  c.launches++;
+}
+
+void nm_sell_clone(const NmParcsr& src, NmParcsr& dst) {
+  const NmSell& S = src.sell;
+  NmSell& D = dst.sell;
+  D.nchunk = 0;
+  if (S.nchunk == 0) return;
+  NmCtx& c = nm_ctx();
+  auto cp = [&](auto& d, const auto& s) {
+    d.alloc(s.n);
+    NM_CUDA(cudaMemcpyAsync(d.p, s.p, s.n * sizeof(*s.p), cudaMemcpyDeviceToDevice, c.stream));
+  };
+  D.val.alloc(S.val.n);
+  cp(D.col, S.col); cp(D.off, S.off); cp(D.rows, S.rows); cp(D.rowlen, S.rowlen); cp(D.chunks, S.chunks);
+  cp(D.slot_src, S.slot_src);
+  D.nslot = S.nslot; D.bytes = S.bytes; D.nchunk = S.nchunk;
+  nm_sell_fill_from(dst, D);
 }

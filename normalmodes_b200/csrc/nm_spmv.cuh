@@ -342,6 +342,104 @@ __global__ void __launch_bounds__(NM_SPMV_THREADS, 3) k_pack(NmPackArgs A, Epi e
   }
 }
 
+// ================================================================ sliced-JDS kernel (no staging, no barriers)
+struct NmSellArgs {
+  const NmSellChunk* chunks;
+  const double* val;
+  const int* col;
+  const int* off;
+  const int* rows;
+  const int* rowlen;
+  const double* x;
+  const double* xg;
+  int ncol;
+};
+
+// One thread block per slice; thread = (scalar row of the slice, lane l of L).  Values and column ids are read
+// straight from global memory: in JDS order the lanes of a warp (neighbouring rows, same step) read neighbouring
+// words, so the matrix stream is coalesced without shared memory, the kernel runs at full occupancy and every lane
+// keeps 4 independent x gathers in flight.  L adjacent lanes share a long row (shuffle butterfly, fixed order).
+template <int FMT, class Epi>
+__global__ void __launch_bounds__(NM_SPMV_THREADS) k_sell(NmSellArgs A, Epi epi) {
+  constexpr int R = (FMT == NM_FMT_CSR) ? 1 : 3;
+  const NmSellChunk d = A.chunks[blockIdx.x];
+  const int L = d.L;
+  const int slot = threadIdx.x / L, l = threadIdx.x - slot * L;
+  const bool active = slot < R * d.nr;
+  const int r = active ? slot / R : 0, comp = slot - R * (slot / R);
+  const int len = active ? A.rowlen[d.r0 + r] : 0;
+  const int row = R * A.rows[d.r0 + r] + comp;
+  typename Epi::In in;
+  if (active && l == 0) in = epi.load(row);
+  const int* __restrict__ off = A.off + d.o0;
+  const int* __restrict__ col = A.col + d.e0;
+  const double* __restrict__ x = A.x;
+  const double* __restrict__ xg = A.xg;
+  const int ncol = A.ncol;
+  double acc = 0.0;
+  if (FMT == NM_FMT_ROW3) {
+    // scalar row 3r+comp: 3 consecutive values per block column at ((e0 + p)*9 + comp*3)
+    const double* __restrict__ val = A.val + 9 * d.e0 + 3 * comp;
+    double b0 = 0.0, b1 = 0.0;
+    int k = l;
+    for (; k + L < len; k += 2 * L) {
+      const int pa = off[k] + r, pb = off[k + L] + r;
+      const int ca = 3 * col[pa], cb = 3 * col[pb];
+      const double* va = val + 9 * (size_t)pa;
+      const double* vb = val + 9 * (size_t)pb;
+      const double xa0 = nm_ldx(x, xg, ncol, ca), xa1 = nm_ldx(x, xg, ncol, ca + 1), xa2 = nm_ldx(x, xg, ncol, ca + 2);
+      const double xb0 = nm_ldx(x, xg, ncol, cb), xb1 = nm_ldx(x, xg, ncol, cb + 1), xb2 = nm_ldx(x, xg, ncol, cb + 2);
+      b0 += va[0] * xa0; b0 += va[1] * xa1; b0 += va[2] * xa2;
+      b1 += vb[0] * xb0; b1 += vb[1] * xb1; b1 += vb[2] * xb2;
+    }
+    if (k < len) {
+      const int pa = off[k] + r;
+      const int ca = 3 * col[pa];
+      const double* va = val + 9 * (size_t)pa;
+      b0 += va[0] * nm_ldx(x, xg, ncol, ca); b0 += va[1] * nm_ldx(x, xg, ncol, ca + 1); b0 += va[2] * nm_ldx(x, xg, ncol, ca + 2);
+    }
+    acc = b0 + b1;
+  } else {
+    const double* __restrict__ val = A.val + d.e0;
+    double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+    int k = l;
+    for (; k + 3 * L < len; k += 4 * L) {
+      const int p0 = off[k] + r, p1 = off[k + L] + r, p2 = off[k + 2 * L] + r, p3 = off[k + 3 * L] + r;
+      int c0 = col[p0], c1 = col[p1], c2 = col[p2], c3 = col[p3];
+      if (FMT == NM_FMT_KRON3) { c0 = 3 * c0 + comp; c1 = 3 * c1 + comp; c2 = 3 * c2 + comp; c3 = 3 * c3 + comp; }
+      const double v0 = val[p0], v1 = val[p1], v2 = val[p2], v3 = val[p3];
+      const double x0 = nm_ldx(x, xg, ncol, c0), x1 = nm_ldx(x, xg, ncol, c1), x2 = nm_ldx(x, xg, ncol, c2),
+                   x3 = nm_ldx(x, xg, ncol, c3);
+      b0 += v0 * x0; b1 += v1 * x1; b2 += v2 * x2; b3 += v3 * x3;
+    }
+    for (; k < len; k += L) {
+      const int p0 = off[k] + r;
+      int c0 = col[p0];
+      if (FMT == NM_FMT_KRON3) c0 = 3 * c0 + comp;
+      b0 += val[p0] * nm_ldx(x, xg, ncol, c0);
+    }
+    acc = (b0 + b1) + (b2 + b3);
+  }
+  for (int o = L >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (active && l == 0) epi.apply(row, acc, in);
+}
+
+template <int FMT, class Epi>
+static inline void nm_sell_launch(NmParcsr& M, NmSell& S, const double* x, const Epi& epi) {
+  NmCtx& c = nm_ctx();
+  NmSellArgs A;
+  A.chunks = S.chunks.p; A.val = S.val.p; A.col = S.col.p; A.off = S.off.p; A.rows = S.rows.p; A.rowlen = S.rowlen.p;
+  A.x = x; A.xg = M.halo.xg.p ? M.halo.xg.p : x; A.ncol = M.ncol;
+  k_sell<FMT, Epi><<<S.nchunk, NM_SPMV_THREADS, 0, c.stream>>>(A, epi);
+  c.launches++;
+}
+template <class Epi>
+static inline void nm_sell_dispatch(NmParcsr& M, NmSell& S, const double* x, const Epi& epi) {
+  if (M.format == NM_FMT_KRON3) nm_sell_launch<NM_FMT_KRON3, Epi>(M, S, x, epi);
+  else if (M.format == NM_FMT_ROW3) nm_sell_launch<NM_FMT_ROW3, Epi>(M, S, x, epi);
+  else nm_sell_launch<NM_FMT_CSR, Epi>(M, S, x, epi);
+}
+
 // ---------------------------------------------------------------- fallback kernels (global-memory subwarp per row)
 template <int W, class Epi>
 __global__ void __launch_bounds__(NM_SPMV_THREADS)
@@ -457,6 +555,11 @@ static inline void nm_pack_launch(NmParcsr& M, NmPack& P, const double* x, const
 
 // Product through an explicit pack (NmChebIter's pack-order copy): x and the epilogue vectors are in P's order.
 template <class Epi>
+static inline void nm_spmv_sell_epi(NmParcsr& M, NmSell& S, const double* x, const Epi& epi, const int* send_idx) {
+  nm_halo_exchange(M, x, send_idx);
+  nm_sell_dispatch(M, S, x, epi);
+}
+template <class Epi>
 static inline void nm_spmv_pack_epi(NmParcsr& M, NmPack& P, const double* x, const Epi& epi, const int* send_idx) {
   nm_halo_exchange(M, x, send_idx);
   if (M.format == NM_FMT_KRON3) nm_pack_launch<NM_FMT_KRON3, Epi>(M, P, x, epi);
@@ -468,6 +571,7 @@ static inline void nm_spmv_pack_epi(NmParcsr& M, NmPack& P, const double* x, con
 template <class Epi>
 static inline void nm_spmv_epi(NmParcsr& M, const double* x, const Epi& epi) {
   nm_halo_exchange(M, x);
+  if (M.sell.nchunk > 0) { nm_sell_dispatch(M, M.sell, x, epi); return; }
   if (M.pack.nchunk > 0) {
     if (M.format == NM_FMT_KRON3) nm_pack_launch<NM_FMT_KRON3, Epi>(M, M.pack, x, epi);
     else if (M.format == NM_FMT_ROW3) nm_pack_launch<NM_FMT_ROW3, Epi>(M, M.pack, x, epi);

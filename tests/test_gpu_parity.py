@@ -305,13 +305,19 @@ def test_error_paths(nm):
         mv.chebiter_setup(-1.0, 2.0, 5, h)
 
 
-@pytest.mark.parametrize("entries,distinct,maxgrid,stages", [(0, 0, 0, 2), (256, 64, 2, 2), (512, 4096, 3, 1), (96, 40, 1, 4)])
-def test_packed_kernel_ring_and_chunking(nm, monkeypatch, entries, distinct, maxgrid, stages):
+@pytest.mark.parametrize("sell,entries,distinct,maxgrid,stages", [(1, 0, 0, 0, 2), (1, 4, 0, 0, 2), (1, 1000, 0, 0, 2),
+                                                                  (0, 0, 0, 0, 2), (0, 256, 64, 2, 2),
+                                                                  (0, 512, 4096, 3, 1), (0, 96, 40, 1, 4)])
+def test_packed_kernel_ring_and_chunking(nm, monkeypatch, sell, entries, distinct, maxgrid, stages):
     """TMA-staged packed row-block kernel (k_pack) against the oracle product for the three formats, with chunk
     sizes / grid limits that force many chunks per CTA (ring wrap-around, mbarrier phase flips, L = 1..32 lanes per
     row) and against the global-memory fallback kernels; fused ChebIter epilogue included."""
     from oracle import fem, solver
     from normalmodes_b200 import matvec as mv
+    monkeypatch.setenv("NM_NATURAL_PACK", "1")             # packs are only built inside NmChebIter by default
+    monkeypatch.setenv("NM_KERNEL_SELL", str(sell))        # 1: sliced-JDS kernel (k_sell, entries = NM_SELL_TARGET)
+    if sell and entries:
+        monkeypatch.setenv("NM_SELL_TARGET", str(entries))
     if entries:
         monkeypatch.setenv("NM_PACK_ENTRIES", str(entries))
         monkeypatch.setenv("NM_PACK_DISTINCT", str(distinct))
@@ -324,18 +330,18 @@ def test_packed_kernel_ring_and_chunking(nm, monkeypatch, entries, distinct, max
         for k, m in to_coomat(c["mats"]).items():
             S = fem.to_scipy(c["mats"][k])
             x = rng.uniform(-1, 1, S.shape[1])
-            monkeypatch.setenv("NM_NO_PACK", "0")
+            monkeypatch.setenv("NM_NO_PACK", "0"); monkeypatch.setenv("NM_NO_SELL", "0")
             h = mv.parcsr_create(m)
             y = mv.parcsr_matvec(h, x, S.shape[0])
             nm.nm_parcsr_free(h)
             assert (np.abs(y - S @ x) <= _spmv_tol(S, x)).all(), (name, k)
-            monkeypatch.setenv("NM_NO_PACK", "1")
+            monkeypatch.setenv("NM_NO_PACK", "1"); monkeypatch.setenv("NM_NO_SELL", "1")
             h = mv.parcsr_create(m)
             y2 = mv.parcsr_matvec(h, x, S.shape[0])
             nm.nm_parcsr_free(h)
             assert (np.abs(y - y2) <= 2 * _spmv_tol(S, x)).all(), (name, k)
     # fused Chebyshev step through the packed kernel (KRON3 B~)
-    monkeypatch.setenv("NM_NO_PACK", "0")
+    monkeypatch.setenv("NM_NO_PACK", "0"); monkeypatch.setenv("NM_NO_SELL", "0")
     c = load_case("const3k_p2_j1")
     m = to_coomat(c["mats"])["B"]
     h = mv.parcsr_create(m)

@@ -50,9 +50,10 @@ def main():
                                                                      [int(v) for v in a.ctas.split(",")]))
         for vb, dc, st, ct in combos:
             if vb is None:
-                os.environ["NM_NO_PACK"] = "1"
+                os.environ["NM_NO_PACK"] = "1"; os.environ["NM_NO_SELL"] = "1"
             else:
-                os.environ["NM_NO_PACK"] = "0"
+                os.environ["NM_NO_PACK"] = "0"; os.environ["NM_NO_SELL"] = "0"
+                os.environ["NM_SELL_TARGET"] = str(dc)
                 os.environ["NM_PACK_ENTRIES"] = str(vb // 6 if which in ("Ad", "A") else vb)
                 os.environ["NM_PACK_DISTINCT"] = str(dc // 3 if which in ("Ad", "A") else dc)
                 os.environ["NM_PACK_STAGES"] = str(st)
