@@ -55,8 +55,13 @@ int nm_chebiter_free(void* cheb);
 int nm_chebiter_solve_host(void* cheb, const double* b, double* x);
 int nm_chebiter_solve_dev(void* cheb, const double* b_dev, double* x_dev);
 int nm_chebiter_stats(void* cheb, long long* nsolve, long long* nmatvec, int* deg, double* lmin, double* lmax);
-/* kind: 0 plain kernels, 1 TMA-staged packed kernel, 2 sliced JDS; bytes: matrix bytes one step streams */
+/* kind: 0 plain kernels, 1 TMA-staged packed kernel, 2 sliced JDS, 3 warp-sliced ELL slabs (k_slab);
+   bytes: matrix bytes one step streams */
 int nm_chebiter_pack_info(void* cheb, int* kind, long long* bytes);
+/* host-only self-test of the slab packer (no GPU): packs the pattern, walks the blobs as k_slab does and returns
+   y = A x in pack order, the pack order and {nchunk, grid, threads, smem_bytes, nstage, max_chunks_per_cta, padded} */
+int nm_slab_host_selftest(int n, int ncolb, int R, const int* rp, const int* idx, const double* vals, const double* x,
+                          double* y, int* order_out, int* info);
 
 /* ---- operators: the callbacks sparseAV / sparsefsAV / sparseBV / sparseApV (mod_matvec.f90:445-520) ---- */
 int nm_op_create_csr(void* mat, void** op_out);                               /* w = M v                        */

@@ -5,7 +5,7 @@
 // zero initial guess; no inner products.  Each step is ONE kernel: the SpMV r -= M d with the
 // x += d and d = a d + b r updates in its epilogue (EpiCheb), so a step streams M once and touches
 // each vector once.
-#include "nm_spmv.cuh"
+#include "nm_slab.cuh"
 #include <algorithm>
 
 // The iteration keeps its vectors in the PACK ORDER of a second, permuted copy of M (nm_pack_build_into): every
@@ -37,7 +37,14 @@ static void cheb_build_ppack(NmChebIter& C) {
   idx.resize(rp[n]);
   (blk ? M.bja : M.ja).download(idx.data(), idx.size());
   const int* order_dev = nullptr;
-  if (nm_use_sell()) {
+  // NM_CHEB_KERNEL: slab (default; k_slab, thread per index row) | pack (k_pack) | sell (k_sell)
+  const char* kk = getenv("NM_CHEB_KERNEL");
+  const bool want_slab = !(kk && kk[0]) ? !nm_use_sell() : (strcmp(kk, "slab") == 0);
+  const bool want_sell = (kk && kk[0]) ? (strcmp(kk, "sell") == 0) : nm_use_sell();
+  if (want_slab) nm_slab_build_into(M, C.pslab, rp, idx, n);
+  if (C.pslab.nchunk > 0) {
+    order_dev = C.pslab.order.p;
+  } else if (want_sell) {
     nm_sell_build_into(M, C.psell, rp, idx, n, true);
     if (C.psell.nchunk == 0) return;
     order_dev = C.psell.order.p;
@@ -85,13 +92,13 @@ void nm_chebiter_solve(NmChebIter& C, const double* b, double* x) {
   NmParcsr& M = *C.M;
   NmCtx& c = nm_ctx();
   double* dbuf[2] = {C.d0.p, C.d1.p};
-  const bool perm = C.ppack.nchunk > 0 || C.psell.nchunk > 0;
-  const int* order_dev = C.psell.nchunk > 0 ? C.psell.order.p : C.ppack.order.p;
+  const bool perm = C.ppack.nchunk > 0 || C.psell.nchunk > 0 || C.pslab.nchunk > 0;
+  const int* order_dev = C.pslab.nchunk > 0 ? C.pslab.order.p : (C.psell.nchunk > 0 ? C.psell.order.p : C.ppack.order.p);
   const int nblk = M.format == NM_FMT_KRON3 ? M.nbrow : M.nrow, R = M.format == NM_FMT_KRON3 ? 3 : 1;
   double* xout = x;
   if (perm) {
     if (C.ppack_version != M.values_version) {
-      nm_pack_fill_from(M, C.ppack); nm_sell_fill_from(M, C.psell);
+      nm_pack_fill_from(M, C.ppack); nm_sell_fill_from(M, C.psell); nm_slab_fill_from(M, C.pslab);
       C.ppack_version = M.values_version;
     }
     k_perm_gather<<<nm_div_up(M.nrow, 256), 256, 0, c.stream>>>(C.bp.p, b, order_dev, nblk, R);
@@ -109,7 +116,8 @@ void nm_chebiter_solve(NmChebIter& C, const double* b, double* x) {
     e.d_out = dbuf[k & 1];
     e.x = x;
     e.inv_theta = 1.0 / C.theta; e.ak = C.ak[k]; e.bk = C.bk[k];
-    if (C.psell.nchunk > 0) nm_spmv_sell_epi(M, C.psell, din, e, C.send_idx_p.p);
+    if (C.pslab.nchunk > 0) nm_spmv_slab_epi(M, C.pslab, din, e, C.send_idx_p.p);
+    else if (C.psell.nchunk > 0) nm_spmv_sell_epi(M, C.psell, din, e, C.send_idx_p.p);
     else if (perm) nm_spmv_pack_epi(M, C.ppack, din, e, C.send_idx_p.p);
     else nm_spmv_epi(M, din, e);
     din = dbuf[k & 1];
@@ -152,13 +160,13 @@ extern "C" int nm_chebiter_solve_dev(void* h, const double* b_dev, double* x_dev
   NM_API_END
 }
 // kind: 0 = plain kernels on the caller's numbering, 1 = TMA-staged packed kernel (k_pack), 2 = sliced JDS (k_sell),
-// both on vectors kept in pack order; bytes = matrix bytes one iteration step streams
+// 3 = TMA-staged warp-sliced ELL slabs (k_slab), all three on vectors kept in pack order; bytes = matrix bytes one iteration step streams
 extern "C" int nm_chebiter_pack_info(void* h, int* kind, long long* bytes) {
   NM_API_BEGIN
   NmChebIter& C = *(NmChebIter*)h;
-  const int k = C.psell.nchunk > 0 ? 2 : (C.ppack.nchunk > 0 ? 1 : 0);
+  const int k = C.pslab.nchunk > 0 ? 3 : (C.psell.nchunk > 0 ? 2 : (C.ppack.nchunk > 0 ? 1 : 0));
   if (kind) *kind = k;
-  if (bytes) *bytes = k == 2 ? C.psell.bytes : (k == 1 ? C.ppack.bytes : C.M->fmt_bytes);
+  if (bytes) *bytes = k == 3 ? C.pslab.bytes : (k == 2 ? C.psell.bytes : (k == 1 ? C.ppack.bytes : C.M->fmt_bytes));
   NM_API_END
 }
 extern "C" int nm_chebiter_stats(void* h, long long* nsolve, long long* nmatvec, int* deg, double* lmin, double* lmax) {

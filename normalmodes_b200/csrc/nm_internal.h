@@ -154,6 +154,30 @@ struct NmSell {
   DBuf<int> order;                        // permuted: position -> caller's index row
 };
 
+// Warp-sliced ELL slabs in pack order (k_slab, nm_slab.cuh / nm_slab.cu): index rows grouped breadth-first into
+// compact chunks of at most T lanes (T = threads per CTA); a row of up to NM_SLAB_SPLIT entries is walked by ONE
+// thread, a longer one by an aligned group of 2, 4, ... lanes (combined by shuffles); lanes are grouped into
+// slices of 32 (one warp), each padded to its longest lane, entries step-major -> stride-32 conflict-free
+// shared-memory reads, row sums in registers, no partial sums in memory, no offsets table.
+// A chunk is one contiguous 16-byte aligned blob (header, slice table, values, distinct column ids, 16-bit
+// chunk-local column indices) moved by one TMA bulk copy.  Vectors live in pack order (row j of chunk c is
+// element first(c)+j).
+struct NmSlabHeader { int nr, nd, nslice, first, nep, gmax, pad1, pad2; };   // 32 bytes; gmax: most lanes per row
+struct NmSlab {
+  DBuf<unsigned char> blob;
+  DBuf<NmPackDesc> desc;
+  DBuf<int> cta_first;                    // grid+1: first chunk of each CTA (balanced by bytes)
+  DBuf<unsigned> slot_off8;
+  DBuf<int> slot_src;
+  long long nslot = 0;
+  int nchunk = 0;                         // 0: not built
+  int grid = 0, threads = 0, max_chunks_per_cta = 0;
+  int stage_bytes = 0, xs_doubles = 0, nstage = 0, smem_bytes = 0;
+  long long bytes = 0;                    // blob bytes = what one product streams
+  long long entries = 0, padded_entries = 0;
+  DBuf<int> order;                        // pack position -> caller's index row
+};
+
 struct NmParcsr {
   int nrow_glob = 0, ncol_glob = 0;
   int nrow = 0, ncol = 0;                 // local (owned) rows / columns
@@ -185,6 +209,7 @@ struct NmChebIter {
   // pack-order copy of M (nm_pack_build_into, permuted): the iteration runs on vectors kept in that order
   NmPack ppack;
   NmSell psell;
+  NmSlab pslab;
   long long ppack_version = -1;
   DBuf<double> bp, xp;                    // b and x in pack order
   DBuf<int> send_idx_p;                   // halo send list in pack order
@@ -255,6 +280,10 @@ void nm_sell_build_into(NmParcsr& M, NmSell& S, const std::vector<int>& rp, cons
                         bool permuted);
 void nm_sell_fill_from(NmParcsr& M, NmSell& S);
 void nm_sell_clone(const NmParcsr& src, NmParcsr& dst);
+void nm_slab_build_into(NmParcsr& M, NmSlab& S, const std::vector<int>& rp, const std::vector<int>& idx, int n);
+void nm_slab_fill_from(NmParcsr& M, NmSlab& S);
+void nm_cm_order(int n, const std::vector<int>& rp, const std::vector<int>& idx, std::vector<int>& order);
+int nm_env_int(const char* name, int dflt);
 bool nm_use_sell();                                                    // NM_KERNEL_SELL (default 1): k_sell instead of k_pack
 void nm_pack_clone(const NmParcsr& src, NmParcsr& dst);                // same structure, values from dst
 // chebiter

@@ -18,10 +18,11 @@
 #include <numeric>
 #include <queue>
 
-static int env_int_(const char* name, int dflt) {
+int nm_env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && v[0]) ? atoi(v) : dflt;
 }
+static int env_int_(const char* name, int dflt) { return nm_env_int(name, dflt); }
 
 // Cuthill-McKee order of the rows of a square pattern (columns >= n, i.e. ghosts, are ignored).
 static void cm_order(int n, const std::vector<int>& rp, const std::vector<int>& idx, std::vector<int>& order) {
@@ -52,6 +53,10 @@ static void cm_order(int n, const std::vector<int>& rp, const std::vector<int>& 
       order.insert(order.end(), nb.begin(), nb.end());
     }
   }
+}
+
+void nm_cm_order(int n, const std::vector<int>& rp, const std::vector<int>& idx, std::vector<int>& order) {
+  cm_order(n, rp, idx, order);
 }
 
 bool nm_use_sell() { return env_int_("NM_KERNEL_SELL", 0) != 0; }

@@ -1,0 +1,439 @@
+// Host-side construction of the warp-sliced ELL slabs streamed by k_slab (nm_slab.cuh).
+//
+// Stores exactly the matrix handed to pevsl_parcsrcreate_f90 (src/mod_matvec.f90:69-71,146-148) after the Jacobi
+// scaling of Bdiagscaling / Apdiagscaling (:252-441): nothing dropped or approximated.  Only the ORDER changes:
+//   1. index rows (nodes for B = M (x) I3, scalar rows for Ap~) are ordered by a Cuthill-McKee sweep so that
+//      consecutive rows share columns; the iteration's vectors live in that order (NmChebIter permutes b in and
+//      x out once per solve);
+//   2. the order is cut into chunks of at most T rows (T = threads per CTA), bounded by padded entries (stage
+//      size) and DISTINCT columns (the x values a chunk needs are staged once in shared memory);
+//   3. inside a chunk rows are sorted by length (stable) and grouped into slices of 32; a slice is padded to its
+//      longest row and stored step-major: entry k of lane j at eoff + 32 k + j (conflict-free LDS);
+//   4. column ids become 16-bit indices into the chunk's ascending distinct-column list;
+//   5. the order of the entries INSIDE a row (free: it only reassociates the row sum, deterministically) is picked
+//      so that the 16 lanes of a half-warp gather x from 16 different shared-memory bank pairs.
+// Per entry the stream is 8 (value) + 2 (index) bytes plus ~0.8 byte of column list, against 12 for CSR.
+#include "nm_slab.cuh"
+#include <algorithm>
+#include <numeric>
+
+static inline size_t up16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+// Everything the device needs, built on the host (no CUDA calls: also driven by the CPU tests through
+// nm_slab_host_selftest).
+struct NmSlabHost {
+  std::vector<unsigned char> blob;
+  std::vector<NmPackDesc> desc;
+  std::vector<int> cta_first, slot_src, order;
+  std::vector<unsigned> slot_off8;
+  int nchunk = 0, grid = 0, threads = 0, max_chunks_per_cta = 0, stage_bytes = 0, xs_doubles = 0, nstage = 0, smem_bytes = 0;
+  long long padded_entries = 0;
+};
+
+// rp/idx: row pointers and column ids (< ncolb) of the n index rows; R scalar rows/columns per index entry;
+// sm_count: SMs of the device the launch geometry is made for.  Returns false when the matrix is not packable.
+static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std::vector<int>& idx, int n, int R,
+                            int ncolb, int sm_count) {
+  H.nchunk = 0;
+  int T = nm_env_int("NM_SLAB_THREADS", 128);
+  if (T != 64 && T != 128 && T != 256) T = 128;
+  const int lcap = std::max(4, nm_env_int("NM_SLAB_SPLIT", 32));               // entries one thread walks at most
+  const int ecap = std::max(32, nm_env_int("NM_SLAB_ENTRIES", 26 * T));        // (estimated) padded entries per chunk
+  const int dcap = std::max(16, std::min(16384, nm_env_int("NM_SLAB_DISTINCT", R == 3 ? 5 * T : 12 * T)));
+  auto len_of = [&](int row) { return rp[row + 1] - rp[row]; };
+  // lanes a row is split over: the next power of two >= len / lcap (1, 2, 4, ... 32)
+  auto lanes_of = [&](int len) { int g = 1; while (g < 32 && g * lcap < len) g *= 2; return g; };
+  // ---- 1+2. row order and chunks in one sweep: a chunk is grown breadth-first from a seed over the rows not
+  // yet placed (a compact blob of mesh neighbours: its rows share most of their columns, so the DISTINCT columns
+  // staged per chunk stay few), until T lanes, the entry cap or the distinct-column cap is reached; the next
+  // seed comes from the frontier left behind, so consecutive chunks are neighbours as well.
+  struct Chunk { int first, nr, nd; };
+  std::vector<Chunk> chunks;
+  std::vector<int> order;
+  order.reserve(n);
+  {
+    const bool grow = nm_env_int("NM_PACK_ORDER", 1) != 0;
+    std::vector<int> stamp(ncolb, -1);
+    std::vector<char> placed(n, 0), queued(n, 0);
+    std::vector<int> frontier, q;
+    size_t fhead = 0;
+    int scan = 0, id = 0;
+    while ((int)order.size() < n) {
+      Chunk c{(int)order.size(), 0, 0};
+      int lanes = 0, ne = 0;
+      bool full = false;
+      q.clear();
+      size_t qhead = 0;
+      while (!full) {
+        if (qhead == q.size()) {                    // (re)seed: frontier first, then the lowest unplaced row
+          int seed = -1;
+          while (grow && fhead < frontier.size()) {
+            const int v = frontier[fhead++];
+            if (!placed[v] && !queued[v]) { seed = v; break; }
+          }
+          if (seed < 0) {
+            while (scan < n && (placed[scan] || queued[scan])) ++scan;
+            if (scan == n) break;
+            seed = scan;
+          }
+          queued[seed] = 1;
+          q.push_back(seed);
+        }
+        const int row = q[qhead];
+        const int len = len_of(row), g = lanes_of(len);
+        if (len > 32 * lcap) return false;            // a row longer than a warp can split: not packable
+        int fresh = 0;
+        for (int p = rp[row]; p < rp[row + 1]; ++p) if (stamp[idx[p]] != id) ++fresh;
+        const int est = g * ((len + g - 1) / g);
+        if (c.nr > 0 && (lanes + g > T || ne + est > ecap || c.nd + fresh > dcap)) { full = true; break; }
+        if (g > T || fresh > dcap) return false;
+        ++qhead;
+        for (int p = rp[row]; p < rp[row + 1]; ++p) stamp[idx[p]] = id;
+        c.nd += fresh; ne += est; lanes += g; c.nr++;
+        placed[row] = 1;
+        order.push_back(row);
+        if (grow)
+          for (int p = rp[row]; p < rp[row + 1]; ++p) {
+            const int v = idx[p];
+            if (v < n && !placed[v] && !queued[v]) { queued[v] = 1; q.push_back(v); }
+          }
+      }
+      for (size_t i = qhead; i < q.size(); ++i) { queued[q[i]] = 0; frontier.push_back(q[i]); }
+      if (c.nr == 0) return false;
+      if (c.nd > 65535) return false;
+      ++id;
+      chunks.push_back(c);
+    }
+  }
+  // ---- 2b. final row order inside a chunk: classes of equal lane count, widest class first (so every group of g
+  // lanes starts at a multiple of g), longest lane-length first inside a class (stable)
+  std::vector<int> final_order(n), newid(n);
+  auto vlen_of = [&](int row) { const int len = len_of(row), g = lanes_of(len); return (len + g - 1) / g; };
+  for (const Chunk& c : chunks) {
+    std::copy(order.begin() + c.first, order.begin() + c.first + c.nr, final_order.begin() + c.first);
+    std::stable_sort(final_order.begin() + c.first, final_order.begin() + c.first + c.nr, [&](int a, int b) {
+      const int ga = lanes_of(len_of(a)), gb = lanes_of(len_of(b));
+      if (ga != gb) return ga > gb;
+      return vlen_of(a) > vlen_of(b);
+    });
+  }
+  for (int i = 0; i < n; ++i) newid[final_order[i]] = i;
+  auto colid = [&](int c) { return c < n ? newid[c] : c; };                  // ghosts (>= n) keep their id
+  // ---- 3. blobs.  Lane t of a chunk walks one SEGMENT of a row; slice s = lanes 32s..32s+31 (one warp), padded
+  // to its longest segment.
+  const int nchunk = (int)chunks.size();
+  std::vector<NmPackDesc> desc(nchunk);
+  std::vector<size_t> start(nchunk);
+  std::vector<int> nep_of(nchunk), nlane_of(nchunk);
+  size_t total = 0, max_blob = 0;
+  int max_nd = 0;
+  long long pentries = 0;
+  for (int i = 0; i < nchunk; ++i) {
+    const Chunk& c = chunks[i];
+    const int* rows = final_order.data() + c.first;
+    int lanes = 0, nep = 0, wmax = 0;
+    for (int j = 0; j < c.nr; ++j) {
+      const int g = lanes_of(len_of(rows[j])), v = vlen_of(rows[j]);
+      for (int l = 0; l < g; ++l, ++lanes) {
+        if (lanes % 32 == 0) { nep += 32 * wmax; wmax = 0; }
+        wmax = std::max(wmax, v);
+      }
+    }
+    nep += 32 * wmax;
+    NM_REQUIRE(lanes <= T, "slab: chunk with %d lanes", lanes);
+    nep_of[i] = nep; nlane_of[i] = lanes;
+    const int nslice = (lanes + 31) / 32;
+    size_t b = 32 + up16(8 * (size_t)nslice) + 8 * (size_t)nep + 4 * (size_t)c.nd + 2 * (size_t)nep + 2 * (size_t)(32 * nslice);
+    b = up16(b);
+    start[i] = total;
+    desc[i].off16 = (unsigned)(total / 16);
+    desc[i].bytes = (unsigned)b;
+    total += b;
+    max_blob = std::max(max_blob, b);
+    max_nd = std::max(max_nd, c.nd);
+    pentries += nep;
+  }
+  NM_REQUIRE(total / 16 < 0xffffffffull && (total + 7) / 8 < 0xffffffffull, "slab: matrix too large for 32-bit offsets");
+  std::vector<unsigned char>& blob = H.blob;
+  blob.assign(total, 0);
+  std::vector<unsigned>& slot_off8 = H.slot_off8;
+  std::vector<int>& slot_src = H.slot_src;
+  slot_off8.clear(); slot_src.clear();
+  slot_off8.reserve((size_t)rp[n]);
+  slot_src.reserve((size_t)rp[n]);
+  std::vector<int> cols, lidx_of(ncolb, -1), lane_row(T), lane_w(T);
+  std::vector<std::vector<int>> rem;
+  const bool bank_aware = nm_env_int("NM_PACK_BANK_AWARE", 1) != 0;
+  for (int i = 0; i < nchunk; ++i) {
+    const Chunk& c = chunks[i];
+    unsigned char* base = blob.data() + start[i];
+    const int nlane = nlane_of[i], nslice = (nlane + 31) / 32, nep = nep_of[i];
+    const int* rows = final_order.data() + c.first;
+    // lane -> local row, and the per-lane word of the kernel: log2(lanes of the row) << 12 | local row (leader
+    // lane of a group) or 0xfff (other lanes and padding lanes)
+    int gmax = 1;
+    {
+      int t = 0;
+      for (int j = 0; j < c.nr; ++j) {
+        const int g = lanes_of(len_of(rows[j]));
+        gmax = std::max(gmax, g);
+        NM_REQUIRE(t % g == 0, "slab: group of %d lanes at lane %d", g, t);
+        for (int l = 0; l < g; ++l) lane_row[t++] = j;
+      }
+      NM_REQUIRE(t == nlane, "slab: lane count");
+    }
+    NmSlabHeader h{c.nr, c.nd, nslice, c.first, nep, gmax, 0, 0};
+    memcpy(base, &h, sizeof(h));
+    const size_t o_tbl = 32;
+    const size_t o_val = 32 + up16(8 * (size_t)nslice);
+    const size_t o_cols = o_val + 8 * (size_t)nep;
+    const size_t o_idx = o_cols + 4 * (size_t)c.nd;
+    const size_t o_lane = o_idx + 2 * (size_t)nep;
+    unsigned* tbl = (unsigned*)(base + o_tbl);
+    int* bcols = (int*)(base + o_cols);
+    unsigned short* bidx = (unsigned short*)(base + o_idx);
+    unsigned short* blane = (unsigned short*)(base + o_lane);
+    for (int t = 0; t < 32 * nslice; ++t) blane[t] = 0x0fff;
+    for (int t = 0; t < nlane; ++t) {
+      const int j = lane_row[t];
+      const int g = lanes_of(len_of(rows[j]));
+      int lg = 0;
+      while ((1 << lg) < g) ++lg;
+      const bool leader = (t == 0 || lane_row[t - 1] != j);
+      blane[t] = (unsigned short)((lg << 12) | (leader ? j : 0x0fff));
+    }
+    // distinct columns, ascending in the numbering the vectors use (neighbouring ids share cache lines)
+    cols.clear();
+    for (int j = 0; j < c.nr; ++j)
+      for (int p = rp[rows[j]]; p < rp[rows[j] + 1]; ++p)
+        if (lidx_of[idx[p]] < 0) { lidx_of[idx[p]] = 0; cols.push_back(idx[p]); }
+    std::sort(cols.begin(), cols.end(), [&](int a, int b) { return colid(a) < colid(b); });
+    NM_REQUIRE((int)cols.size() == c.nd, "slab: distinct-column count mismatch");
+    for (int j = 0; j < c.nd; ++j) { lidx_of[cols[j]] = j; bcols[j] = colid(cols[j]); }
+    const size_t val8 = (start[i] + o_val) / 8;                   // blob position of the value region in doubles
+    // entries still to be placed, per local row (shared by the lanes of the row's group)
+    if ((int)rem.size() < c.nr) rem.resize(c.nr);
+    for (int j = 0; j < c.nr; ++j) {
+      rem[j].clear();
+      for (int p = rp[rows[j] + 1] - 1; p >= rp[rows[j]]; --p) rem[j].push_back(p);    // back() = first in CSR order
+    }
+    int eoff = 0;
+    for (int s = 0; s < nslice; ++s) {
+      const int t0 = 32 * s, nl = std::min(32, nlane - t0);
+      int w = 0;
+      for (int l = 0; l < nl; ++l) w = std::max(w, vlen_of(rows[lane_row[t0 + l]]));
+      tbl[2 * s] = (unsigned)eoff;
+      tbl[2 * s + 1] = (unsigned)w;
+      for (int k = 0; k < w; ++k)
+        for (int h0 = 0; h0 < 32; h0 += 16) {
+          unsigned taken = 0, was_real = 0;
+          // real entries first, then the padding lanes take bank pairs that are still free
+          for (int l = h0; l < h0 + 16; ++l) {
+            if (l >= nl) continue;
+            std::vector<int>& rj = rem[lane_row[t0 + l]];
+            if (rj.empty()) continue;
+            was_real |= 1u << (l - h0);
+            const int p = eoff + 32 * k + l;
+            int pick = (int)rj.size() - 1;
+            if (bank_aware)
+              for (int q = (int)rj.size() - 1; q >= 0; --q)
+                if (!(taken & (1u << (lidx_of[idx[rj[q]]] & 15)))) { pick = q; break; }
+            const int src = rj[pick];
+            rj.erase(rj.begin() + pick);
+            const int li = lidx_of[idx[src]];
+            taken |= 1u << (li & 15);
+            bidx[p] = (unsigned short)li;
+            slot_off8.push_back((unsigned)(val8 + p));
+            slot_src.push_back(src);
+          }
+          for (int l = h0; l < h0 + 16; ++l) {
+            if (was_real & (1u << (l - h0))) continue;
+            // padding: value stays 0.0; point it at a free bank pair (any valid local column)
+            int li = 0;
+            for (int q = 0; q < 16 && q < c.nd; ++q)
+              if (!(taken & (1u << q))) { li = q; break; }
+            taken |= 1u << (li & 15);
+            bidx[eoff + 32 * k + l] = (unsigned short)li;
+          }
+        }
+      eoff += 32 * w;
+    }
+    for (int j = 0; j < c.nr; ++j) NM_REQUIRE(rem[j].empty(), "slab: row longer than its lanes");
+    NM_REQUIRE(eoff == nep, "slab: padded entry count mismatch");
+    for (int j = 0; j < c.nd; ++j) lidx_of[cols[j]] = -1;
+  }
+  // ---- 4. launch geometry: CTAs get contiguous chunk ranges of ~equal bytes
+  H.threads = T;
+  H.xs_doubles = R * max_nd;
+  H.stage_bytes = (int)up16(max_blob);
+  H.nstage = std::max(1, std::min(8, nm_env_int("NM_SLAB_STAGES", 2)));
+  const int fixed = NM_SLAB_MAXDESC * (int)sizeof(NmPackDesc) + 64 + 16 * H.xs_doubles;
+  const int budget = 226 * 1024;
+  while (H.nstage > 1 && (int)up16(fixed) + H.nstage * H.stage_bytes > budget) H.nstage--;
+  H.smem_bytes = (int)up16(fixed) + H.nstage * H.stage_bytes;
+  if (H.smem_bytes > budget) return false;
+  const int fit = std::max(1, (228 * 1024) / (H.smem_bytes + 1024));          // 1 KB reserved per CTA
+  const int per_sm = std::max(1, std::min(fit, nm_env_int("NM_SLAB_CTAS_PER_SM", fit)));
+  int grid = std::min(nchunk, sm_count * per_sm);
+  grid = std::max(1, std::min(grid, nm_env_int("NM_SLAB_MAXGRID", grid)));     // tests: force several chunks per CTA
+  const int maxper = std::min(NM_SLAB_MAXDESC, T);
+  grid = std::max(grid, nm_div_up(nchunk, maxper));
+  H.cta_first.assign(grid + 1, 0);
+  H.max_chunks_per_cta = 0;
+  {
+    // balanced contiguous split by bytes: every CTA gets 1..maxper chunks
+    int ci = 0;
+    size_t done = 0;
+    for (int g = 0; g < grid; ++g) {
+      H.cta_first[g] = ci;
+      const size_t target = (size_t)((double)total * (g + 1) / grid);
+      const int after = grid - g - 1;                                  // CTAs still to be served
+      int cnt = 1;
+      done += desc[ci].bytes;
+      while (ci + cnt < nchunk - after && cnt < maxper) {
+        const bool forced = (long long)(nchunk - (ci + cnt)) > (long long)after * maxper;
+        if (!forced && done + desc[ci + cnt].bytes / 2 > target) break;
+        done += desc[ci + cnt].bytes;
+        ++cnt;
+      }
+      ci += cnt;
+      H.max_chunks_per_cta = std::max(H.max_chunks_per_cta, cnt);
+    }
+    H.cta_first[grid] = ci;
+    NM_REQUIRE(ci == nchunk, "slab: chunk split lost chunks (%d of %d)", ci, nchunk);
+  }
+  H.grid = grid;
+  H.padded_entries = pentries;
+  H.desc = desc;
+  H.order = final_order;
+  H.nchunk = nchunk;
+  return true;
+}
+
+void nm_slab_build_into(NmParcsr& M, NmSlab& S, const std::vector<int>& rp, const std::vector<int>& idx, int n) {
+  S.nchunk = 0;
+  if (n == 0 || M.nrow != M.ncol || M.format == NM_FMT_ROW3) return;
+  const int R = M.format == NM_FMT_CSR ? 1 : 3;
+  const int ncolb = (M.ncol + M.halo.nghost + R - 1) / R;                     // column ids are < ncolb
+  NmSlabHost H;
+  if (!slab_build_host(H, rp, idx, n, R, ncolb, nm_ctx().sm_count)) return;
+  S.threads = H.threads; S.xs_doubles = H.xs_doubles; S.stage_bytes = H.stage_bytes; S.nstage = H.nstage;
+  S.smem_bytes = H.smem_bytes; S.grid = H.grid; S.max_chunks_per_cta = H.max_chunks_per_cta;
+  S.bytes = (long long)H.blob.size();
+  S.entries = (long long)H.slot_src.size(); S.padded_entries = H.padded_entries;
+  S.nslot = (long long)H.slot_src.size();
+  S.blob.alloc(H.blob.size()); S.blob.upload(H.blob.data(), H.blob.size());
+  S.desc.from_host(H.desc);
+  S.cta_first.from_host(H.cta_first);
+  S.slot_off8.from_host(H.slot_off8);
+  S.slot_src.from_host(H.slot_src);
+  S.order.from_host(H.order);
+  S.nchunk = H.nchunk;
+  nm_slab_fill_from(M, S);
+}
+
+// CPU self-test hook (no GPU needed): packs the n x ncolb index pattern with R scalar components per entry, fills
+// the values, then WALKS THE BLOBS exactly as k_slab does (same decode, same slice / lane / step order, same ring
+// and CTA assignment) to form y = A x in pack order.  Returns the pack order and geometry for the caller to check.
+extern "C" int nm_slab_host_selftest(int n, int ncolb, int R, const int* rp_, const int* idx_, const double* vals,
+                                     const double* x /* R*ncolb */, double* y /* R*n, pack order */, int* order_out,
+                                     int* info /* 8: nchunk, grid, threads, smem_bytes, nstage, max_chunks_per_cta, padded, sum nd */) {
+  NM_API_BEGIN
+  std::vector<int> rp(rp_, rp_ + n + 1), idx(idx_, idx_ + rp_[n]);
+  NmSlabHost H;
+  NM_REQUIRE(slab_build_host(H, rp, idx, n, R, ncolb, 148), "slab: not packable");
+  double* blob8 = (double*)H.blob.data();
+  for (size_t i = 0; i < H.slot_src.size(); ++i) blob8[H.slot_off8[i]] = vals[H.slot_src[i]];
+  std::vector<int> newid(n);
+  for (int i = 0; i < n; ++i) newid[H.order[i]] = i;
+  std::vector<char> seen(n, 0);
+  std::vector<double> xs;
+  for (int g = 0; g < H.grid; ++g) {
+    NM_REQUIRE(H.cta_first[g + 1] - H.cta_first[g] >= 1 && H.cta_first[g + 1] - H.cta_first[g] <= std::min(NM_SLAB_MAXDESC, H.threads),
+               "slab: CTA %d has %d chunks", g, H.cta_first[g + 1] - H.cta_first[g]);
+    for (int ci = H.cta_first[g]; ci < H.cta_first[g + 1]; ++ci) {
+      const unsigned char* st = H.blob.data() + 16ull * H.desc[ci].off16;
+      NM_REQUIRE((int)H.desc[ci].bytes <= H.stage_bytes && H.desc[ci].bytes % 16 == 0, "slab: blob size");
+      const NmSlabHeader h = *(const NmSlabHeader*)st;
+      const unsigned* tbl = (const unsigned*)(st + 32);
+      const double* sv = (const double*)(st + 32 + ((8 * h.nslice + 15) & ~15));
+      const int* scols = (const int*)(sv + h.nep);
+      const unsigned short* sidx = (const unsigned short*)(scols + h.nd);
+      NM_REQUIRE(h.nr >= 1 && h.nr <= 32 * h.nslice && 32 * h.nslice <= H.threads && R * h.nd <= H.xs_doubles, "slab: header");
+      NM_REQUIRE((const unsigned char*)(sidx + h.nep) <= st + H.desc[ci].bytes, "slab: blob overrun");
+      xs.assign((size_t)R * h.nd, 0.0);
+      for (int j = 0; j < R * h.nd; ++j) {
+        const int node = j / R;
+        // columns are in the vectors' numbering (pack order for owned columns): x is given in the CALLER's order
+        const int c = scols[node];
+        NM_REQUIRE(c >= 0 && c < ncolb, "slab: column id");
+        const int orig = c < n ? H.order[c] : c;
+        xs[j] = x[(size_t)R * orig + (j - R * node)];
+      }
+      const unsigned short* slane = sidx + h.nep;
+      NM_REQUIRE((const unsigned char*)(slane + 32 * h.nslice) <= st + H.desc[ci].bytes, "slab: blob overrun (lanes)");
+      int owners = 0;
+      for (int warp = 0; warp < H.threads / 32; ++warp) {
+        double acc[32][3];
+        unsigned lw[32];
+        for (int lane = 0; lane < 32; ++lane) {
+          acc[lane][0] = acc[lane][1] = acc[lane][2] = 0.0;
+          lw[lane] = warp < h.nslice ? slane[32 * warp + lane] : 0x0fffu;
+          if (warp < h.nslice) {
+            const unsigned eoff = tbl[2 * warp], w = tbl[2 * warp + 1];
+            for (unsigned k = 0; k < w; ++k) {
+              const double m = sv[eoff + 32 * k + lane];
+              const int li = sidx[eoff + 32 * k + lane];
+              NM_REQUIRE(li < h.nd, "slab: local index");
+              for (int c = 0; c < R; ++c) acc[lane][c] += m * xs[(size_t)R * li + c];
+            }
+          }
+        }
+        for (int o = 1; o < h.gmax; o <<= 1) {                 // __shfl_down_sync semantics (out of range: own value)
+          double nxt[32][3];
+          for (int lane = 0; lane < 32; ++lane)
+            for (int c = 0; c < R; ++c) {
+              const double other = lane + o < 32 ? acc[lane + o][c] : acc[lane][c];
+              nxt[lane][c] = ((1 << (lw[lane] >> 12)) > o) ? acc[lane][c] + other : acc[lane][c];
+            }
+          memcpy(acc, nxt, sizeof(acc));
+        }
+        for (int lane = 0; lane < 32; ++lane) {
+          const unsigned rank = lw[lane] & 0xfffu;
+          if (rank == 0xfffu) continue;
+          NM_REQUIRE((int)rank < h.nr, "slab: local row %u of %d", rank, h.nr);
+          const int row = h.first + (int)rank;
+          NM_REQUIRE(row >= 0 && row < n && !seen[row], "slab: row %d visited twice or out of range", row);
+          seen[row] = 1;
+          ++owners;
+          for (int c = 0; c < R; ++c) y[(size_t)R * row + c] = acc[lane][c];
+        }
+      }
+      NM_REQUIRE(owners == h.nr, "slab: %d leader lanes for %d rows", owners, h.nr);
+    }
+  }
+  for (int i = 0; i < n; ++i) NM_REQUIRE(seen[i], "slab: row %d never visited", i);
+  if (order_out) std::copy(H.order.begin(), H.order.end(), order_out);
+  if (info) {
+    info[0] = H.nchunk; info[1] = H.grid; info[2] = H.threads; info[3] = H.smem_bytes; info[4] = H.nstage;
+    info[5] = H.max_chunks_per_cta; info[6] = (int)std::min<long long>(H.padded_entries, 0x7fffffff);
+    long long snd = 0;
+    for (int ci = 0; ci < H.nchunk; ++ci) snd += ((const NmSlabHeader*)(H.blob.data() + 16ull * H.desc[ci].off16))->nd;
+    info[7] = (int)std::min<long long>(snd, 0x7fffffff);                     // sum of distinct columns over chunks
+  }
+  NM_API_END
+}
+
+__global__ void k_slab_fill(long long nslot, const unsigned* __restrict__ off8, const int* __restrict__ src,
+                            const double* __restrict__ vals, double* __restrict__ blob) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < nslot) blob[off8[i]] = vals[src[i]];
+}
+
+void nm_slab_fill_from(NmParcsr& M, NmSlab& S) {
+  if (S.nchunk == 0 || S.nslot == 0) return;
+  NmCtx& c = nm_ctx();
+  const double* vals = M.format == NM_FMT_KRON3 ? M.mval.p : M.a.p;
+  k_slab_fill<<<nm_div_up(S.nslot, 256), 256, 0, c.stream>>>(S.nslot, S.slot_off8.p, S.slot_src.p, vals, (double*)S.blob.p);
+  c.launches++;
+}

@@ -26,6 +26,9 @@ def main():
     p.add_argument("--job", type=int, default=2)
     p.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "kernel_times.json"))
     p.add_argument("--reps", type=int, default=20)
+    p.add_argument("--ncu-range", action="store_true",
+                   help="only run [cudaProfilerStart; one Ap~ solve; one B~ solve; cudaProfilerStop] after warm-up (for "
+                        "ncu --profile-from-start off --kernel-name-base demangled -k regex:k_pack --launch-skip/-c)")
     a = p.parse_args()
     import torch
     torch.cuda.set_device(0)
@@ -54,6 +57,24 @@ def main():
         e1.record(stream)
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) * 1e3 / (reps * per)
+
+    if a.ncu_range:
+        solveB = lambda: _lib.check(L.nm_chebiter_solve_dev(mv.chebB, C.c_void_p(z.data_ptr()), C.c_void_p(y.data_ptr())))
+        zp = torch.empty(max(mv.Ap.siz(0), 1) if fem.fluidcase else 1, dtype=torch.float64, device="cuda").uniform_(-1, 1, generator=g)
+        yp = torch.empty_like(zp)
+        solveAp = lambda: _lib.check(L.nm_chebiter_solve_dev(mv.chebAp, C.c_void_p(zp.data_ptr()), C.c_void_p(yp.data_ptr())))
+        for _ in range(2):
+            if fem.fluidcase:
+                solveAp()
+            solveB()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        if fem.fluidcase:
+            solveAp()
+        solveB()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
 
     res = {}
 
