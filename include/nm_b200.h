@@ -48,6 +48,10 @@ int nm_parcsr_info(void* mat, int* nrow, int* ncol, long long* nnz, int* format,
  * d_i = 1/sqrt(sign*M_ii), M~_ij = (sign*M_ij*d_j)*d_i ; d_host[n_local] receives d (may be NULL). */
 int nm_parcsr_jacobi_scale(void* mat, double sign, double* d_host);
 int nm_parcsr_get_values(void* mat, double* a_host /* nnz_local */);
+/* host-only (no GPU, no communicator): receive side of one rank's halo plan -- sorted ghost column ids (ghost_glob may
+   be null) and the number owned by each rank; the device plan of nm_parcsr_create is built from the same routine */
+int nm_halo_plan_host(int nranks, int rank, const int* col_starts, long long nnz, const int* ja, int* nghost,
+                      int* ghost_glob, int* recv_cnt);
 
 /* ---- ChebIter: pevsl_setup_chebiter_f90 / pevsl_chebiter_f90 (mod_matvec.f90:93,174,480,512) ---- */
 int nm_chebiter_create(double lmin, double lmax, int deg, void* mat, void** cheb_out);

@@ -59,10 +59,21 @@ struct NmCtx {
   double* h_pin = nullptr;        // small pinned host scratch
   size_t h_pin_cap = 0;
   long launches = 0;              // kernels launched by this library (bench 'gpu_launches')
+  // NVLink peer window (one process per GPU, CUDA IPC): ghost buffers and arrival flags of every matrix live in
+  // one device allocation per rank that all peers map, so the halo exchange is direct peer stores + a flag
+  // (k_halo_push, nm_parcsr.cu) instead of NCCL send/recv.  p2p == false: NCCL fallback.
+  bool p2p = false;
+  unsigned char* win = nullptr;   // this rank's window
+  size_t win_bytes = 0, win_used = 0;
+  std::vector<unsigned char*> peer_win;   // peer_win[r]: rank r's window mapped here (peer_win[rank] = win)
+  unsigned* push_ctr = nullptr;   // last-block detection counter of k_halo_push (device)
+  int* dev_status = nullptr;      // device-side error word (bit 0: halo flag wait timed out)
 };
 NmCtx& nm_ctx();
 void nm_ensure_init();
 double* nm_red_scratch(size_t n);
+size_t nm_win_alloc(size_t bytes);          // bump allocation in the peer window (256-byte aligned), collective order
+void nm_check_device_status();              // raises if a device-side wait timed out
 double* nm_pinned(size_t n);
 
 template <class T>
@@ -113,6 +124,15 @@ struct NmHalo {
   DBuf<int> send_idx;                     // local (owned) column ids to pack, device
   DBuf<double> sendbuf;                   // device
   DBuf<double> xg;                        // ghost values, device (gather target c >= ncol -> xg[c-ncol])
+  double* xg_cur = nullptr;               // ghost buffer the kernels read after the last exchange (xg.p or a window half)
+  // peer-store exchange (NmCtx::p2p): two ghost buffers (parity of the exchange counter) + one arrival flag per
+  // source rank in this rank's window; where this rank's values go in every peer's window
+  size_t win_xg[2] = {0, 0}, win_flag = 0;             // byte offsets in this rank's window
+  std::vector<size_t> peer_xg[2], peer_flag;           // per peer: byte offsets in THAT peer's window
+  std::vector<int> peer_base;                           // per peer: where this rank's block starts in its ghost tail
+  std::vector<int> cnt_all;                             // P x P: cnt_all[r*P+s] = ghosts rank r receives from rank s
+  unsigned long long epoch = 0;                         // exchanges done (flag value of the next one = epoch + 1)
+  bool p2p = false;
 };
 
 // Packed row-block format of the streaming SpMV (nm_spmv.cuh / nm_pack.cu).  The (block-)rows are ordered for

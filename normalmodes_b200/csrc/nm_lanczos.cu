@@ -282,6 +282,7 @@ void nm_lanbounds(NmPevsl& P, int mlan, int lanstep, double tol, double* lmin_ou
     if (r1 + r2 < tol * (fabs(lmin) + fabs(lmax))) break;
   }
   NM_CUDA(cudaStreamSynchronize(nm_ctx().stream));
+  nm_check_device_status();
   *lmin_out = lmin; *lmax_out = lmax;
 }
 
@@ -417,6 +418,7 @@ void nm_cheblannr(NmPevsl& P, const double xintv[4], int maxit, double tol, cons
     for (int i = 0; i < P.nev; ++i) nm_vec_copy(P.Y.p + (size_t)i * n, U.p + (size_t)keep[i] * n, n);
     NM_CUDA(cudaStreamSynchronize(ctx.stream));
   }
+  nm_check_device_status();
   P.t_filter = t_filter; P.t_reorth = t_reorth; P.t_ritz = now_s() - t_r0; P.t_total = now_s() - t_begin;
 }
 

@@ -11,10 +11,84 @@ __global__ void k_pack(double* __restrict__ buf, const double* __restrict__ x, c
   if (i < n) buf[i] = x[idx[i]];
 }
 
+// Peer-store exchange (NVLink, CUDA IPC window): every rank writes the x values its peers need straight into THEIR
+// ghost buffers, then raises an arrival flag per destination; the last block of the same kernel waits for the
+// flags of the ranks that write to us, so the next kernel on the stream may gather from the ghost buffer.  Two
+// ghost buffers alternate (parity of the exchange counter): a peer can be at most one exchange ahead, because its
+// next push follows its wait for OUR flag of the current one, which we raise only after our previous product.
+struct NmPushArgs {
+  int nranks, me, nsend;
+  int send_off[9];
+  double* peer_xg[8];                       // destination of this rank's block in each peer's ghost buffer (parity applied)
+  unsigned long long* peer_flag[8];         // this rank's slot in each peer's flag array
+  const unsigned long long* my_flag;        // flag array of this rank (slot s written by rank s)
+  unsigned recv_mask, send_mask;
+  unsigned long long epoch;
+  unsigned* ctr;
+  int* status;
+};
+
+__global__ void k_halo_push(NmPushArgs A, const double* __restrict__ x, const int* __restrict__ idx) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.nsend; i += gridDim.x * blockDim.x) {
+    int r = 0;
+    while (i >= A.send_off[r + 1]) ++r;
+    A.peer_xg[r][i - A.send_off[r]] = x[idx[i]];
+  }
+  __threadfence_system();
+  __shared__ int last;
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(A.ctr, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence_system();                    // every block's stores are ordered before the flags below
+  const int r = threadIdx.x;
+  if (r < A.nranks && r != A.me) {
+    if (A.send_mask & (1u << r)) {
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.peer_flag[r]), "l"(A.epoch) : "memory");
+    }
+    if (A.recv_mask & (1u << r)) {
+      const unsigned long long* f = A.my_flag + r;
+      unsigned long long v;
+      const long long t0 = clock64();
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+        if (v >= A.epoch) break;
+        if (clock64() - t0 > 20000000000ll) { atomicOr(A.status, 1); break; }     // ~10 s: peer stalled or died
+      }
+    }
+  }
+  if (threadIdx.x == 0) *A.ctr = 0;
+}
+
 void nm_halo_exchange(NmParcsr& M, const double* x, const int* send_idx) {
   NmCtx& c = nm_ctx();
   NmHalo& h = M.halo;
   if (c.nranks == 1 || (h.nghost == 0 && h.nsend == 0)) return;
+  if (h.p2p) {
+    const unsigned long long epoch = ++h.epoch;
+    const int par = (int)(epoch & 1);
+    NmPushArgs A;
+    A.nranks = c.nranks; A.me = c.rank; A.nsend = h.nsend;
+    A.recv_mask = A.send_mask = 0;
+    for (int r = 0; r < 8; ++r) { A.peer_xg[r] = nullptr; A.peer_flag[r] = nullptr; }
+    for (int r = 0; r <= 8; ++r) A.send_off[r] = r <= c.nranks ? h.send_off[std::min(r, c.nranks)] : h.nsend;
+    for (int r = 0; r < c.nranks; ++r) {
+      if (r == c.rank) continue;
+      if (h.send_cnt[r] > 0) {
+        A.send_mask |= 1u << r;
+        A.peer_xg[r] = (double*)(c.peer_win[r] + h.peer_xg[par][r]) + h.peer_base[r];
+        A.peer_flag[r] = (unsigned long long*)(c.peer_win[r] + h.peer_flag[r]) + c.rank;
+      }
+      if (h.recv_cnt[r] > 0) A.recv_mask |= 1u << r;
+    }
+    A.my_flag = (const unsigned long long*)(c.win + h.win_flag);
+    A.epoch = epoch; A.ctr = c.push_ctr; A.status = c.dev_status;
+    const int blocks = std::max(1, std::min(32, nm_div_up(h.nsend, 256)));
+    k_halo_push<<<blocks, 256, 0, c.stream>>>(A, x, send_idx ? send_idx : h.send_idx.p);
+    c.launches++;
+    h.xg_cur = (double*)(c.win + h.win_xg[par]);
+    return;
+  }
   if (h.nsend > 0) {
     k_pack<<<nm_div_up(h.nsend, 256), 256, 0, c.stream>>>(h.sendbuf.p, x, send_idx ? send_idx : h.send_idx.p, h.nsend);
     c.launches++;
@@ -28,6 +102,71 @@ void nm_halo_exchange(NmParcsr& M, const double* x, const int* send_idx) {
       NM_NCCL(ncclRecv(h.xg.p + h.recv_off[r], h.recv_cnt[r], ncclDouble, r, c.nccl, c.stream));
   }
   NM_NCCL(ncclGroupEnd());
+  h.xg_cur = h.xg.p;
+}
+
+// Window slots of one matrix' halo (collective: every rank calls this for the same matrices in the same order).
+// cnt: P x P matrix, cnt[r*P + s] = ghosts rank r receives from rank s.
+static void halo_p2p_setup(NmHalo& h, const std::vector<int>& cnt) {
+  NmCtx& c = nm_ctx();
+  h.p2p = false;
+  if (!c.p2p) return;
+  const int P = c.nranks;
+  const size_t gb = (size_t)std::max(h.nghost, 1) * sizeof(double);
+  long long mine[3];
+  h.win_xg[0] = nm_win_alloc(gb); h.win_xg[1] = nm_win_alloc(gb);
+  h.win_flag = nm_win_alloc(sizeof(unsigned long long) * 8);
+  mine[0] = (long long)h.win_xg[0]; mine[1] = (long long)h.win_xg[1]; mine[2] = (long long)h.win_flag;
+  DBuf<long long> d_mine(3), d_all((size_t)3 * P);
+  d_mine.upload(mine, 3);
+  NM_NCCL(ncclAllGather(d_mine.p, d_all.p, 3, ncclInt64, c.nccl, c.stream));
+  std::vector<long long> all((size_t)3 * P);
+  d_all.download(all.data(), all.size());
+  h.peer_xg[0].assign(P, 0); h.peer_xg[1].assign(P, 0); h.peer_flag.assign(P, 0); h.peer_base.assign(P, 0);
+  for (int r = 0; r < P; ++r) {
+    h.peer_xg[0][r] = (size_t)all[3 * r]; h.peer_xg[1][r] = (size_t)all[3 * r + 1]; h.peer_flag[r] = (size_t)all[3 * r + 2];
+    int base = 0;                                   // ghosts of rank r are grouped by owner: blocks of ranks < me first
+    for (int s2 = 0; s2 < c.rank; ++s2) base += cnt[(size_t)r * P + s2];
+    h.peer_base[r] = base;
+  }
+  h.epoch = 0;
+  h.p2p = true;
+  h.xg_cur = (double*)(c.win + h.win_xg[0]);
+}
+
+// Host part of the plan (no device, no communicator): the sorted unique global ids of the columns a rank's block
+// references outside its own range [lo, hi) -- sorted by id = grouped by owner rank.
+static void halo_ghosts_host(int ncol_glob, int lo, int hi, long long nnz, const int* ja, std::vector<int>& gl) {
+  gl.clear();
+  for (long long p = 0; p < nnz; ++p) {
+    const int g = ja[p];
+    NM_REQUIRE(g >= 0 && g < ncol_glob, "parcsrcreate: column id %d out of range (0-based global ids expected)", g);
+    if (g < lo || g >= hi) gl.push_back(g);
+  }
+  std::sort(gl.begin(), gl.end());
+  gl.erase(std::unique(gl.begin(), gl.end()), gl.end());
+}
+static int halo_owner(const int* col_starts, int P, int g) {
+  return (int)(std::upper_bound(col_starts, col_starts + P + 1, g) - col_starts) - 1;
+}
+
+// Host-only view of the receive side of a rank's halo plan, for hosts and tests without a GPU: ghost ids (sorted)
+// and how many come from each owner.  ghost_glob may be null (count only) or hold up to nnz ids.
+extern "C" int nm_halo_plan_host(int nranks, int rank, const int* col_starts, long long nnz, const int* ja, int* nghost,
+                                 int* ghost_glob, int* recv_cnt) {
+  NM_API_BEGIN
+  NM_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "halo_plan_host: bad rank %d of %d", rank, nranks);
+  std::vector<int> gl;
+  halo_ghosts_host(col_starts[nranks], col_starts[rank], col_starts[rank + 1], nnz, ja, gl);
+  for (int r = 0; r < nranks; ++r) recv_cnt[r] = 0;
+  for (int g : gl) {
+    const int owner = halo_owner(col_starts, nranks, g);
+    NM_REQUIRE(owner >= 0 && owner < nranks && owner != rank, "ghost column %d has no remote owner", g);
+    recv_cnt[owner]++;
+  }
+  *nghost = (int)gl.size();
+  if (ghost_glob) std::copy(gl.begin(), gl.end(), ghost_glob);
+  NM_API_END
 }
 
 // Build the send side of the plan: every rank tells every owner which of its columns it needs.
@@ -38,7 +177,7 @@ static void build_halo_plan(NmParcsr& M, const int* col_starts) {
   h.recv_cnt.assign(P, 0); h.recv_off.assign(P + 1, 0);
   h.send_cnt.assign(P, 0); h.send_off.assign(P + 1, 0);
   for (int g : h.ghost_glob) {
-    int owner = (int)(std::upper_bound(col_starts, col_starts + P + 1, g) - col_starts) - 1;
+    const int owner = halo_owner(col_starts, P, g);
     NM_REQUIRE(owner >= 0 && owner < P && owner != c.rank, "ghost column %d has no remote owner", g);
     h.recv_cnt[owner]++;
   }
@@ -51,6 +190,7 @@ static void build_halo_plan(NmParcsr& M, const int* col_starts) {
   NM_NCCL(ncclAllGather(d_mine.p, d_cnt.p, P, ncclInt, c.nccl, c.stream));
   std::vector<int> cnt((size_t)P * P);
   d_cnt.download(cnt.data(), cnt.size());
+  h.cnt_all = cnt;
   for (int r = 0; r < P; ++r) h.send_cnt[r] = cnt[(size_t)r * P + c.rank];      // what rank r needs from me
   for (int r = 0; r < P; ++r) h.send_off[r + 1] = h.send_off[r] + h.send_cnt[r];
   h.nsend = h.send_off[P];
@@ -71,6 +211,7 @@ static void build_halo_plan(NmParcsr& M, const int* col_starts) {
     NM_REQUIRE(sidx[i] >= 0 && sidx[i] < M.ncol, "halo plan: peer asked for a column this rank does not own");
   }
   if (h.nsend) { h.send_idx.alloc(h.nsend); h.send_idx.upload(sidx.data(), h.nsend); h.sendbuf.alloc(h.nsend); }
+  halo_p2p_setup(h, cnt);
 }
 
 // ---------------------------------------------------------------- format detection (host)
@@ -169,13 +310,7 @@ NmParcsr* nm_parcsr_build(int nrow_glob, int ncol_glob, const int* row_starts, c
   // ghost columns: sorted unique global ids outside [col0, col0+ncol)
   std::vector<int>& gl = M->halo.ghost_glob;
   const int lo = M->col0, hi = M->col0 + M->ncol;
-  for (long long p = 0; p < nnz; ++p) {
-    const int g = ja[p];
-    NM_REQUIRE(g >= 0 && g < ncol_glob, "parcsrcreate: column id %d out of range (0-based global ids expected)", g);
-    if (g < lo || g >= hi) gl.push_back(g);
-  }
-  std::sort(gl.begin(), gl.end());
-  gl.erase(std::unique(gl.begin(), gl.end()), gl.end());
+  halo_ghosts_host(ncol_glob, lo, hi, nnz, ja, gl);
   M->halo.nghost = (int)gl.size();
   NM_REQUIRE(c.nranks > 1 || gl.empty(), "parcsrcreate: ghost columns on a single rank");
   std::vector<int> hia(ia, ia + n + 1), hja((size_t)nnz);
@@ -189,6 +324,7 @@ NmParcsr* nm_parcsr_build(int nrow_glob, int ncol_glob, const int* row_starts, c
   M->a.alloc(std::max<size_t>((size_t)nnz, 1)); M->a.upload(a, (size_t)nnz);
   choose_format(*M, hia, hja, a);
   if (M->halo.nghost) M->halo.xg.alloc(M->halo.nghost);
+  M->halo.xg_cur = M->halo.xg.p;
   build_halo_plan(*M, col_starts);
   return M.release();
 }
@@ -232,11 +368,14 @@ NmParcsr* nm_parcsr_scaled_copy(const NmParcsr& M, const double* dr, const doubl
   clone_i(M.halo.send_idx, S->halo.send_idx);
   if (S->halo.nsend) S->halo.sendbuf.alloc(S->halo.nsend);
   if (S->halo.nghost) S->halo.xg.alloc(S->halo.nghost);
+  S->halo.xg_cur = S->halo.xg.p;
+  S->halo.cnt_all = M.halo.cnt_all;
+  if (c.nranks > 1) halo_p2p_setup(S->halo, S->halo.cnt_all);
   // ghost part of the column scaling through the halo plan of the copy
   if (S->halo.nghost > 0 || S->halo.nsend > 0) nm_halo_exchange(*S, dc);
   if (M.nrow) {
     k_scale_csr<<<nm_div_up(M.nrow, 128), 128, 0, c.stream>>>(M.nrow, M.ncol, M.ia.p, M.ja.p, M.a.p, S->a.p, dr, dc,
-                                                              S->halo.xg.p);
+                                                              S->halo.xg_cur);
     c.launches++;
   }
   if (S->format == M.format) {
@@ -304,7 +443,7 @@ extern "C" int nm_parcsr_jacobi_scale(void* h, double sign, double* d_host) {
   NM_REQUIRE(hbad == 0, "jacobi_scale: %d rows without a positive diagonal (sign %g)", hbad, sign);
   nm_halo_exchange(M, d.p);
   if (n) {
-    k_scale_inplace<<<nm_div_up(n, 128), 128, 0, c.stream>>>(n, M.ncol, M.ia.p, M.ja.p, M.a.p, sign, d.p, M.halo.xg.p);
+    k_scale_inplace<<<nm_div_up(n, 128), 128, 0, c.stream>>>(n, M.ncol, M.ia.p, M.ja.p, M.a.p, sign, d.p, M.halo.xg_cur);
     c.launches++;
     if (M.format == NM_FMT_KRON3) {
       k_kron_refresh<<<nm_div_up(M.nbrow, 128), 128, 0, c.stream>>>(M.nbrow, M.bia.p, M.ia.p, M.a.p, M.mval.p);

@@ -98,6 +98,7 @@ extern "C" int nm_sync(void) {
   NM_API_BEGIN
   nm_ensure_init();
   NM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+  nm_check_device_status();
   NM_API_END
 }
 
@@ -111,6 +112,81 @@ extern "C" int nm_comm_unique_id(char* id128) {
   NM_API_END
 }
 
+// ---------------------------------------------------------------- NVLink peer window (CUDA IPC)
+// Every rank allocates one window, publishes its IPC handle through the NCCL communicator and maps the windows
+// of all peers.  All-or-nothing: if any rank fails to map any peer, every rank falls back to NCCL send/recv.
+static void p2p_setup() {
+  NmCtx& c = g_ctx;
+  const char* off = getenv("NM_P2P");
+  int want = !(off && off[0] == '0') && c.nranks <= 8;
+  const size_t bytes = (size_t)std::max(16, nm_env_int("NM_P2P_WINDOW_MB", 256)) << 20;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  int ok = want;
+  if (ok && cudaMalloc((void**)&c.win, bytes) != cudaSuccess) { cudaGetLastError(); c.win = nullptr; ok = 0; }
+  if (ok) {
+    NM_CUDA(cudaMemset(c.win, 0, bytes));
+    if (cudaIpcGetMemHandle(&mine, c.win) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  }
+  // handles + per-rank ok flag in one all-gather (sizeof handle = 64)
+  struct Rec { cudaIpcMemHandle_t h; int ok; int pad[3]; };
+  static_assert(sizeof(Rec) == 80, "Rec layout");
+  Rec rec; rec.h = mine; rec.ok = ok; rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
+  DBuf<unsigned char> d_mine(sizeof(Rec)), d_all(sizeof(Rec) * c.nranks);
+  d_mine.upload((const unsigned char*)&rec, sizeof(Rec));
+  NM_NCCL(ncclAllGather(d_mine.p, d_all.p, sizeof(Rec), ncclChar, c.nccl, c.stream));
+  std::vector<Rec> all(c.nranks);
+  d_all.download((unsigned char*)all.data(), sizeof(Rec) * c.nranks);
+  for (const Rec& r : all) ok = ok && r.ok;
+  c.peer_win.assign(c.nranks, nullptr);
+  if (ok) {
+    for (int r = 0; r < c.nranks; ++r) {
+      if (r == c.rank) { c.peer_win[r] = c.win; continue; }
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+      c.peer_win[r] = (unsigned char*)p;
+    }
+  }
+  // agree: every rank must have mapped every peer
+  DBuf<double> d_ok(1);
+  double v = ok ? 1.0 : 0.0;
+  d_ok.upload(&v, 1);
+  NM_NCCL(ncclAllReduce(d_ok.p, d_ok.p, 1, ncclDouble, ncclMin, c.nccl, c.stream));
+  d_ok.download(&v, 1);
+  if (v < 0.5) {
+    for (int r = 0; r < c.nranks; ++r)
+      if (r != c.rank && c.peer_win[r]) cudaIpcCloseMemHandle(c.peer_win[r]);
+    c.peer_win.clear();
+    if (c.win) cudaFree(c.win);
+    c.win = nullptr; c.p2p = false;
+    if (want && c.rank == 0) fprintf(stderr, "[nm_b200] peer window unavailable: halo exchange falls back to NCCL send/recv\n");
+    return;
+  }
+  c.win_bytes = bytes; c.win_used = 0; c.p2p = true;
+  NM_CUDA(cudaMalloc((void**)&c.push_ctr, 256));
+  NM_CUDA(cudaMemset(c.push_ctr, 0, 256));
+  c.dev_status = (int*)(c.push_ctr + 32);
+}
+
+size_t nm_win_alloc(size_t bytes) {
+  NmCtx& c = g_ctx;
+  NM_REQUIRE(c.p2p, "nm_win_alloc without a peer window");
+  const size_t off = (c.win_used + 255) & ~(size_t)255;
+  NM_REQUIRE(off + bytes <= c.win_bytes, "peer window exhausted (%zu + %zu > %zu bytes): raise NM_P2P_WINDOW_MB", off, bytes,
+             c.win_bytes);
+  c.win_used = off + bytes;
+  return off;
+}
+
+void nm_check_device_status() {
+  NmCtx& c = g_ctx;
+  if (!c.dev_status) return;
+  int st = 0;
+  NM_CUDA(cudaMemcpyAsync(&st, c.dev_status, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  NM_CUDA(cudaStreamSynchronize(c.stream));
+  NM_REQUIRE(st == 0, "device status %d: a halo arrival flag was not seen within the time limit (peer rank stalled or died)", st);
+}
+
 extern "C" int nm_comm_init(int rank, int nranks, const char* id128) {
   NM_API_BEGIN
   nm_ensure_init();
@@ -122,6 +198,7 @@ extern "C" int nm_comm_init(int rank, int nranks, const char* id128) {
     ncclUniqueId id;
     memcpy(&id, id128, 128);
     NM_NCCL(ncclCommInitRank(&g_ctx.nccl, nranks, id, rank));
+    p2p_setup();
   }
   NM_API_END
 }
@@ -130,6 +207,13 @@ extern "C" int nm_comm_finalize(void) {
   NM_API_BEGIN
   if (g_ctx.nccl) {
     NM_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    if (g_ctx.p2p) {
+      for (int r = 0; r < g_ctx.nranks; ++r)
+        if (r != g_ctx.rank && g_ctx.peer_win[r]) cudaIpcCloseMemHandle(g_ctx.peer_win[r]);
+      g_ctx.peer_win.clear();
+      cudaFree(g_ctx.win); cudaFree(g_ctx.push_ctr);
+      g_ctx.win = nullptr; g_ctx.push_ctr = nullptr; g_ctx.dev_status = nullptr; g_ctx.p2p = false;
+    }
     ncclCommDestroy(g_ctx.nccl);
     g_ctx.nccl = nullptr;
   }

@@ -35,32 +35,41 @@ struct NmSlabHost {
 static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std::vector<int>& idx, int n, int R,
                             int ncolb, int sm_count) {
   H.nchunk = 0;
-  int T = nm_env_int("NM_SLAB_THREADS", 128);
-  if (T != 64 && T != 128 && T != 256) T = 128;
-  const int lcap = std::max(4, nm_env_int("NM_SLAB_SPLIT", 32));               // entries one thread walks at most
-  const int ecap = std::max(32, nm_env_int("NM_SLAB_ENTRIES", 26 * T));        // (estimated) padded entries per chunk
-  const int dcap = std::max(16, std::min(16384, nm_env_int("NM_SLAB_DISTINCT", R == 3 ? 5 * T : 12 * T)));
+  int T = nm_env_int("NM_SLAB_THREADS", 256);
+  if (T != 64 && T != 128 && T != 256 && T != 512) T = 256;
+  const int NW = T / 32;
+  const int lcap = std::max(2, nm_env_int("NM_SLAB_SPLIT", 16));               // entries one lane walks at most
+  const int ecap = std::max(32, nm_env_int("NM_SLAB_ENTRIES", 3584));          // (estimated) padded entries per chunk
+  const int dcap = std::max(16, std::min(16384, nm_env_int("NM_SLAB_DISTINCT", R == 3 ? 640 : 1536)));
   auto len_of = [&](int row) { return rp[row + 1] - rp[row]; };
-  // lanes a row is split over: the next power of two >= len / lcap (1, 2, 4, ... 32)
-  auto lanes_of = [&](int len) { int g = 1; while (g < 32 && g * lcap < len) g *= 2; return g; };
+  // lanes a row is shared by (1..32) and the entries each of them walks
+  auto lanes_of = [&](int len) { return std::max(1, (len + lcap - 1) / lcap); };
+  auto vlen_of = [&](int row) { const int len = len_of(row), g = lanes_of(len); return (len + g - 1) / g; };
   // ---- 1+2. row order and chunks in one sweep: a chunk is grown breadth-first from a seed over the rows not
   // yet placed (a compact blob of mesh neighbours: its rows share most of their columns, so the DISTINCT columns
-  // staged per chunk stay few), until T lanes, the entry cap or the distinct-column cap is reached; the next
-  // seed comes from the frontier left behind, so consecutive chunks are neighbours as well.
-  struct Chunk { int first, nr, nd; };
+  // staged per chunk stay few), until its warps are full or the entry / distinct-column cap is reached; the next
+  // seed comes from the frontier left behind, so consecutive chunks are neighbours as well.  A row's lanes must sit
+  // in ONE warp (they are combined by shuffles): rows are placed first-fit into the chunk's T/32 warps, preferring
+  // a warp whose lanes walk the same number of entries (a warp is padded to its longest lane).
+  struct Chunk { int first, nr, nd, nslice, lane_off; };
   std::vector<Chunk> chunks;
-  std::vector<int> order;
+  std::vector<int> order;                   // final row order: chunk after chunk, warp after warp
+  std::vector<short> lane_row_all;          // per chunk 32*nslice lanes: local row (position in the chunk) or -1
   order.reserve(n);
   {
     const bool grow = nm_env_int("NM_PACK_ORDER", 1) != 0;
     std::vector<int> stamp(ncolb, -1);
     std::vector<char> placed(n, 0), queued(n, 0);
     std::vector<int> frontier, q;
+    std::vector<std::vector<int>> bin_rows(NW);
+    std::vector<int> bin_free(NW), bin_vlen(NW);
     size_t fhead = 0;
     int scan = 0, id = 0;
-    while ((int)order.size() < n) {
-      Chunk c{(int)order.size(), 0, 0};
-      int lanes = 0, ne = 0;
+    int nplaced = 0;
+    while (nplaced < n) {
+      Chunk c{nplaced, 0, 0, 0, (int)lane_row_all.size()};
+      int ne = 0;
+      for (int w = 0; w < NW; ++w) { bin_rows[w].clear(); bin_free[w] = 32; bin_vlen[w] = 0; }
       bool full = false;
       q.clear();
       size_t qhead = 0;
@@ -80,70 +89,81 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
           q.push_back(seed);
         }
         const int row = q[qhead];
-        const int len = len_of(row), g = lanes_of(len);
-        if (len > 32 * lcap) return false;            // a row longer than a warp can split: not packable
+        const int len = len_of(row), g = lanes_of(len), v = vlen_of(row);
+        if (g > 32) return false;                     // a row longer than a warp can share: not packable
         int fresh = 0;
         for (int p = rp[row]; p < rp[row + 1]; ++p) if (stamp[idx[p]] != id) ++fresh;
-        const int est = g * ((len + g - 1) / g);
-        if (c.nr > 0 && (lanes + g > T || ne + est > ecap || c.nd + fresh > dcap)) { full = true; break; }
-        if (g > T || fresh > dcap) return false;
+        if (fresh > dcap) return false;
+        // warp for the row: same lane length > empty warp > any warp with room
+        int best = -1, score = -1;
+        for (int w = 0; w < NW; ++w) {
+          if (bin_free[w] < g) continue;
+          const int sc = bin_vlen[w] == v ? 3 : (bin_free[w] == 32 ? 2 : 1);
+          if (sc > score) { score = sc; best = w; }
+        }
+        const int est = g * v;
+        if (best < 0 || (c.nr > 0 && (ne + est > ecap || c.nd + fresh > dcap))) { full = true; break; }
         ++qhead;
         for (int p = rp[row]; p < rp[row + 1]; ++p) stamp[idx[p]] = id;
-        c.nd += fresh; ne += est; lanes += g; c.nr++;
+        c.nd += fresh; ne += est; c.nr++;
+        bin_rows[best].push_back(row); bin_free[best] -= g; bin_vlen[best] = std::max(bin_vlen[best], v);
         placed[row] = 1;
-        order.push_back(row);
+        ++nplaced;
         if (grow)
           for (int p = rp[row]; p < rp[row + 1]; ++p) {
-            const int v = idx[p];
-            if (v < n && !placed[v] && !queued[v]) { queued[v] = 1; q.push_back(v); }
+            const int u = idx[p];
+            if (u < n && !placed[u] && !queued[u]) { queued[u] = 1; q.push_back(u); }
           }
       }
       for (size_t i = qhead; i < q.size(); ++i) { queued[q[i]] = 0; frontier.push_back(q[i]); }
       if (c.nr == 0) return false;
       if (c.nd > 65535) return false;
       ++id;
+      // lanes: non-empty warps, longest lanes first (stable); inside a warp rows in placement order
+      std::vector<int> ws;
+      for (int w = 0; w < NW; ++w) if (!bin_rows[w].empty()) ws.push_back(w);
+      std::stable_sort(ws.begin(), ws.end(), [&](int a, int b) { return bin_vlen[a] > bin_vlen[b]; });
+      c.nslice = (int)ws.size();
+      int local = 0;
+      for (int w : ws) {
+        int used = 0;
+        for (int row : bin_rows[w]) {
+          const int g = lanes_of(len_of(row));
+          for (int l = 0; l < g; ++l) lane_row_all.push_back((short)local);
+          used += g;
+          order.push_back(row);
+          ++local;
+        }
+        for (; used < 32; ++used) lane_row_all.push_back((short)-1);
+      }
       chunks.push_back(c);
     }
   }
-  // ---- 2b. final row order inside a chunk: classes of equal lane count, widest class first (so every group of g
-  // lanes starts at a multiple of g), longest lane-length first inside a class (stable)
-  std::vector<int> final_order(n), newid(n);
-  auto vlen_of = [&](int row) { const int len = len_of(row), g = lanes_of(len); return (len + g - 1) / g; };
-  for (const Chunk& c : chunks) {
-    std::copy(order.begin() + c.first, order.begin() + c.first + c.nr, final_order.begin() + c.first);
-    std::stable_sort(final_order.begin() + c.first, final_order.begin() + c.first + c.nr, [&](int a, int b) {
-      const int ga = lanes_of(len_of(a)), gb = lanes_of(len_of(b));
-      if (ga != gb) return ga > gb;
-      return vlen_of(a) > vlen_of(b);
-    });
-  }
+  std::vector<int>& final_order = order;
+  std::vector<int> newid(n);
   for (int i = 0; i < n; ++i) newid[final_order[i]] = i;
   auto colid = [&](int c) { return c < n ? newid[c] : c; };                  // ghosts (>= n) keep their id
-  // ---- 3. blobs.  Lane t of a chunk walks one SEGMENT of a row; slice s = lanes 32s..32s+31 (one warp), padded
-  // to its longest segment.
+  // ---- 3. blobs.  Lane t of a chunk walks one share of a row; slice s = lanes 32s..32s+31 (one warp), padded
+  // to its longest lane.
   const int nchunk = (int)chunks.size();
   std::vector<NmPackDesc> desc(nchunk);
   std::vector<size_t> start(nchunk);
-  std::vector<int> nep_of(nchunk), nlane_of(nchunk);
+  std::vector<int> nep_of(nchunk);
   size_t total = 0, max_blob = 0;
   int max_nd = 0;
   long long pentries = 0;
   for (int i = 0; i < nchunk; ++i) {
     const Chunk& c = chunks[i];
     const int* rows = final_order.data() + c.first;
-    int lanes = 0, nep = 0, wmax = 0;
-    for (int j = 0; j < c.nr; ++j) {
-      const int g = lanes_of(len_of(rows[j])), v = vlen_of(rows[j]);
-      for (int l = 0; l < g; ++l, ++lanes) {
-        if (lanes % 32 == 0) { nep += 32 * wmax; wmax = 0; }
-        wmax = std::max(wmax, v);
-      }
+    const short* lr = lane_row_all.data() + c.lane_off;
+    int nep = 0;
+    for (int s2 = 0; s2 < c.nslice; ++s2) {
+      int w = 0;
+      for (int l = 0; l < 32; ++l) if (lr[32 * s2 + l] >= 0) w = std::max(w, vlen_of(rows[lr[32 * s2 + l]]));
+      nep += 32 * w;
     }
-    nep += 32 * wmax;
-    NM_REQUIRE(lanes <= T, "slab: chunk with %d lanes", lanes);
-    nep_of[i] = nep; nlane_of[i] = lanes;
-    const int nslice = (lanes + 31) / 32;
-    size_t b = 32 + up16(8 * (size_t)nslice) + 8 * (size_t)nep + 4 * (size_t)c.nd + 2 * (size_t)nep + 2 * (size_t)(32 * nslice);
+    nep_of[i] = nep;
+    size_t b = 32 + up16(8 * (size_t)c.nslice) + 8 * (size_t)nep + 4 * (size_t)c.nd + 2 * (size_t)nep + 2 * (size_t)(32 * c.nslice);
     b = up16(b);
     start[i] = total;
     desc[i].off16 = (unsigned)(total / 16);
@@ -161,27 +181,17 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
   slot_off8.clear(); slot_src.clear();
   slot_off8.reserve((size_t)rp[n]);
   slot_src.reserve((size_t)rp[n]);
-  std::vector<int> cols, lidx_of(ncolb, -1), lane_row(T), lane_w(T);
+  std::vector<int> cols, lidx_of(ncolb, -1);
   std::vector<std::vector<int>> rem;
   const bool bank_aware = nm_env_int("NM_PACK_BANK_AWARE", 1) != 0;
   for (int i = 0; i < nchunk; ++i) {
     const Chunk& c = chunks[i];
     unsigned char* base = blob.data() + start[i];
-    const int nlane = nlane_of[i], nslice = (nlane + 31) / 32, nep = nep_of[i];
+    const int nslice = c.nslice, nep = nep_of[i];
     const int* rows = final_order.data() + c.first;
-    // lane -> local row, and the per-lane word of the kernel: log2(lanes of the row) << 12 | local row (leader
-    // lane of a group) or 0xfff (other lanes and padding lanes)
+    const short* lane_row = lane_row_all.data() + c.lane_off;
     int gmax = 1;
-    {
-      int t = 0;
-      for (int j = 0; j < c.nr; ++j) {
-        const int g = lanes_of(len_of(rows[j]));
-        gmax = std::max(gmax, g);
-        NM_REQUIRE(t % g == 0, "slab: group of %d lanes at lane %d", g, t);
-        for (int l = 0; l < g; ++l) lane_row[t++] = j;
-      }
-      NM_REQUIRE(t == nlane, "slab: lane count");
-    }
+    for (int j = 0; j < c.nr; ++j) gmax = std::max(gmax, lanes_of(len_of(rows[j])));
     NmSlabHeader h{c.nr, c.nd, nslice, c.first, nep, gmax, 0, 0};
     memcpy(base, &h, sizeof(h));
     const size_t o_tbl = 32;
@@ -193,14 +203,17 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
     int* bcols = (int*)(base + o_cols);
     unsigned short* bidx = (unsigned short*)(base + o_idx);
     unsigned short* blane = (unsigned short*)(base + o_lane);
-    for (int t = 0; t < 32 * nslice; ++t) blane[t] = 0x0fff;
-    for (int t = 0; t < nlane; ++t) {
+    // per-lane word of the kernel: bit 15 = first lane of its row (does the epilogue), bits 10..14 = steps s of
+    // the shuffle tree at which lane + 2^s belongs to the same row (add its partial), bits 0..9 = local row
+    for (int t = 0; t < 32 * nslice; ++t) {
       const int j = lane_row[t];
-      const int g = lanes_of(len_of(rows[j]));
-      int lg = 0;
-      while ((1 << lg) < g) ++lg;
-      const bool leader = (t == 0 || lane_row[t - 1] != j);
-      blane[t] = (unsigned short)((lg << 12) | (leader ? j : 0x0fff));
+      if (j < 0) { blane[t] = 0; continue; }
+      const int lane = t & 31;
+      unsigned wd = (unsigned)j & 0x3ffu;
+      if (lane == 0 || lane_row[t - 1] != j) wd |= 0x8000u;
+      for (int s2 = 0; s2 < 5; ++s2)
+        if (lane + (1 << s2) < 32 && lane_row[t + (1 << s2)] == j) wd |= 1u << (10 + s2);
+      blane[t] = (unsigned short)wd;
     }
     // distinct columns, ascending in the numbering the vectors use (neighbouring ids share cache lines)
     cols.clear();
@@ -211,7 +224,7 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
     NM_REQUIRE((int)cols.size() == c.nd, "slab: distinct-column count mismatch");
     for (int j = 0; j < c.nd; ++j) { lidx_of[cols[j]] = j; bcols[j] = colid(cols[j]); }
     const size_t val8 = (start[i] + o_val) / 8;                   // blob position of the value region in doubles
-    // entries still to be placed, per local row (shared by the lanes of the row's group)
+    // entries still to be placed, per local row (shared by the lanes of the row)
     if ((int)rem.size() < c.nr) rem.resize(c.nr);
     for (int j = 0; j < c.nr; ++j) {
       rem[j].clear();
@@ -219,9 +232,9 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
     }
     int eoff = 0;
     for (int s = 0; s < nslice; ++s) {
-      const int t0 = 32 * s, nl = std::min(32, nlane - t0);
+      const int t0 = 32 * s;
       int w = 0;
-      for (int l = 0; l < nl; ++l) w = std::max(w, vlen_of(rows[lane_row[t0 + l]]));
+      for (int l = 0; l < 32; ++l) if (lane_row[t0 + l] >= 0) w = std::max(w, vlen_of(rows[lane_row[t0 + l]]));
       tbl[2 * s] = (unsigned)eoff;
       tbl[2 * s + 1] = (unsigned)w;
       for (int k = 0; k < w; ++k)
@@ -229,7 +242,7 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
           unsigned taken = 0, was_real = 0;
           // real entries first, then the padding lanes take bank pairs that are still free
           for (int l = h0; l < h0 + 16; ++l) {
-            if (l >= nl) continue;
+            if (lane_row[t0 + l] < 0) continue;
             std::vector<int>& rj = rem[lane_row[t0 + l]];
             if (rj.empty()) continue;
             was_real |= 1u << (l - h0);
@@ -266,17 +279,17 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
   H.threads = T;
   H.xs_doubles = R * max_nd;
   H.stage_bytes = (int)up16(max_blob);
-  H.nstage = std::max(1, std::min(8, nm_env_int("NM_SLAB_STAGES", 2)));
+  H.nstage = std::max(2, std::min(8, nm_env_int("NM_SLAB_STAGES", 2)));   // >= 2: blob it+1 is awaited while chunk it is walked
   const int fixed = NM_SLAB_MAXDESC * (int)sizeof(NmPackDesc) + 64 + 16 * H.xs_doubles;
   const int budget = 226 * 1024;
-  while (H.nstage > 1 && (int)up16(fixed) + H.nstage * H.stage_bytes > budget) H.nstage--;
+  while (H.nstage > 2 && (int)up16(fixed) + H.nstage * H.stage_bytes > budget) H.nstage--;
   H.smem_bytes = (int)up16(fixed) + H.nstage * H.stage_bytes;
   if (H.smem_bytes > budget) return false;
   const int fit = std::max(1, (228 * 1024) / (H.smem_bytes + 1024));          // 1 KB reserved per CTA
   const int per_sm = std::max(1, std::min(fit, nm_env_int("NM_SLAB_CTAS_PER_SM", fit)));
   int grid = std::min(nchunk, sm_count * per_sm);
   grid = std::max(1, std::min(grid, nm_env_int("NM_SLAB_MAXGRID", grid)));     // tests: force several chunks per CTA
-  const int maxper = std::min(NM_SLAB_MAXDESC, T);
+  const int maxper = NM_SLAB_MAXDESC;
   grid = std::max(grid, nm_div_up(nchunk, maxper));
   H.cta_first.assign(grid + 1, 0);
   H.max_chunks_per_cta = 0;
@@ -378,7 +391,7 @@ extern "C" int nm_slab_host_selftest(int n, int ncolb, int R, const int* rp_, co
         unsigned lw[32];
         for (int lane = 0; lane < 32; ++lane) {
           acc[lane][0] = acc[lane][1] = acc[lane][2] = 0.0;
-          lw[lane] = warp < h.nslice ? slane[32 * warp + lane] : 0x0fffu;
+          lw[lane] = warp < h.nslice ? slane[32 * warp + lane] : 0u;
           if (warp < h.nslice) {
             const unsigned eoff = tbl[2 * warp], w = tbl[2 * warp + 1];
             for (unsigned k = 0; k < w; ++k) {
@@ -389,18 +402,19 @@ extern "C" int nm_slab_host_selftest(int n, int ncolb, int R, const int* rp_, co
             }
           }
         }
-        for (int o = 1; o < h.gmax; o <<= 1) {                 // __shfl_down_sync semantics (out of range: own value)
+        for (int s2 = 0; (1 << s2) < h.gmax; ++s2) {            // __shfl_down_sync semantics (out of range: own value)
+          const int o = 1 << s2;
           double nxt[32][3];
           for (int lane = 0; lane < 32; ++lane)
             for (int c = 0; c < R; ++c) {
               const double other = lane + o < 32 ? acc[lane + o][c] : acc[lane][c];
-              nxt[lane][c] = ((1 << (lw[lane] >> 12)) > o) ? acc[lane][c] + other : acc[lane][c];
+              nxt[lane][c] = (lw[lane] & (1u << (10 + s2))) ? acc[lane][c] + other : acc[lane][c];
             }
           memcpy(acc, nxt, sizeof(acc));
         }
         for (int lane = 0; lane < 32; ++lane) {
-          const unsigned rank = lw[lane] & 0xfffu;
-          if (rank == 0xfffu) continue;
+          if (!(lw[lane] & 0x8000u)) continue;
+          const unsigned rank = lw[lane] & 0x3ffu;
           NM_REQUIRE((int)rank < h.nr, "slab: local row %u of %d", rank, h.nr);
           const int row = h.first + (int)rank;
           NM_REQUIRE(row >= 0 && row < n && !seen[row], "slab: row %d visited twice or out of range", row);

@@ -34,7 +34,7 @@ struct NmSlabView {
   const double* sv;
   const int* scols;
   const unsigned short* sidx;
-  const unsigned short* slane;   // per lane: log2(lanes of its row) << 12 | local row (group leader) or 0xfff
+  const unsigned short* slane;   // per lane: bit 15 first lane of its row, bits 10..14 shuffle-tree adds, bits 0..9 local row
 };
 __device__ __forceinline__ NmSlabView nm_slab_view(const unsigned char* st) {
   NmSlabView v;
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(T) k_slab(NmSlabArgs A, Epi epi) {
   double* xs0 = (double*)(smem + NM_SLAB_MAXDESC * sizeof(NmPackDesc) + 64);
   unsigned char* stage0 =
       smem + ((NM_SLAB_MAXDESC * sizeof(NmPackDesc) + 64 + 16 * (size_t)A.xs_doubles + 15) & ~(size_t)15);
-  if (tid < nmine) sdesc[tid] = A.desc[c0 + tid];
+  for (int i = tid; i < nmine; i += T) sdesc[i] = A.desc[c0 + i];
   if (tid == 0) {
     for (int s = 0; s < A.nstage; ++s) nm_mbar_init(bars + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -103,10 +103,9 @@ __global__ void __launch_bounds__(T) k_slab(NmSlabArgs A, Epi epi) {
     const double* xs = xs0 + (size_t)(it & 1) * A.xs_doubles;
     if (it + 1 < nmine) gather(it + 1);
     const bool walk = warp < v.h.nslice;
-    const unsigned lw = walk ? (unsigned)v.slane[tid] : 0x0fffu;
-    const int lg = (int)(lw >> 12);
-    const bool own = (lw & 0xfffu) != 0xfffu;                    // leader lane of a row
-    const int row0 = R * (v.h.first + (int)(lw & 0xfffu));
+    const unsigned lw = walk ? (unsigned)v.slane[tid] : 0u;
+    const bool own = (lw & 0x8000u) != 0u;                       // first lane of a row: does its epilogue
+    const int row0 = R * (v.h.first + (int)(lw & 0x3ffu));
     typename Epi::In in[R];
     if (own) {
 #pragma unroll
@@ -128,12 +127,12 @@ __global__ void __launch_bounds__(T) k_slab(NmSlabArgs A, Epi epi) {
         for (int c = 0; c < R; ++c) acc[c] += m * xp[c];
       }
     }
-    // rows split over 2, 4, ... aligned lanes: fixed-order tree sum into the leader lane
-    for (int o = 1; o < v.h.gmax; o <<= 1) {
+    // rows shared by several adjacent lanes of the warp: fixed-order segmented tree sum into the row's first lane
+    for (int s = 0; (1 << s) < v.h.gmax; ++s) {
 #pragma unroll
       for (int c = 0; c < R; ++c) {
-        const double other = __shfl_down_sync(0xffffffffu, acc[c], o);
-        if ((1 << lg) > o) acc[c] += other;
+        const double other = __shfl_down_sync(0xffffffffu, acc[c], 1 << s);
+        if (lw & (1u << (10 + s))) acc[c] += other;
       }
     }
     if (own) {
@@ -151,7 +150,7 @@ static inline void nm_slab_launch_t(NmParcsr& M, NmSlab& S, const double* x, con
   NmCtx& c = nm_ctx();
   NmSlabArgs A;
   A.blob = S.blob.p; A.desc = S.desc.p; A.cta_first = S.cta_first.p;
-  A.x = x; A.xg = M.halo.xg.p ? M.halo.xg.p : x; A.ncol = M.ncol;
+  A.x = x; A.xg = M.halo.xg_cur ? M.halo.xg_cur : x; A.ncol = M.ncol;
   A.stage_bytes = S.stage_bytes; A.xs_doubles = S.xs_doubles; A.nstage = S.nstage;
   static bool attr_set = false;                                  // per template instantiation
   if (!attr_set) {
@@ -167,7 +166,9 @@ template <class Epi>
 static inline void nm_spmv_slab_epi(NmParcsr& M, NmSlab& S, const double* x, const Epi& epi, const int* send_idx) {
   nm_halo_exchange(M, x, send_idx);
   const bool blk = M.format == NM_FMT_KRON3;
-  if (S.threads == 256) {
+  if (S.threads == 512) {
+    if (blk) nm_slab_launch_t<3, 512, Epi>(M, S, x, epi); else nm_slab_launch_t<1, 512, Epi>(M, S, x, epi);
+  } else if (S.threads == 256) {
     if (blk) nm_slab_launch_t<3, 256, Epi>(M, S, x, epi); else nm_slab_launch_t<1, 256, Epi>(M, S, x, epi);
   } else if (S.threads == 64) {
     if (blk) nm_slab_launch_t<3, 64, Epi>(M, S, x, epi); else nm_slab_launch_t<1, 64, Epi>(M, S, x, epi);

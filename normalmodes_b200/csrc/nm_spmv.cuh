@@ -429,7 +429,7 @@ static inline void nm_sell_launch(NmParcsr& M, NmSell& S, const double* x, const
   NmCtx& c = nm_ctx();
   NmSellArgs A;
   A.chunks = S.chunks.p; A.val = S.val.p; A.col = S.col.p; A.off = S.off.p; A.rows = S.rows.p; A.rowlen = S.rowlen.p;
-  A.x = x; A.xg = M.halo.xg.p ? M.halo.xg.p : x; A.ncol = M.ncol;
+  A.x = x; A.xg = M.halo.xg_cur ? M.halo.xg_cur : x; A.ncol = M.ncol;
   k_sell<FMT, Epi><<<S.nchunk, NM_SPMV_THREADS, 0, c.stream>>>(A, epi);
   c.launches++;
 }
@@ -517,7 +517,7 @@ k_spmv_kron3(int nbrow, int ncol, const int* __restrict__ bia, const int* __rest
 template <int W, class Epi>
 static inline void nm_spmv_launch_w(NmParcsr& M, const double* x, const Epi& epi) {
   NmCtx& c = nm_ctx();
-  const double* xg = M.halo.xg.p ? M.halo.xg.p : x;
+  const double* xg = M.halo.xg_cur ? M.halo.xg_cur : x;
   const int per_block = NM_SPMV_THREADS / W;
   if (M.format == NM_FMT_CSR) {
     if (M.nrow == 0) return;
@@ -540,7 +540,7 @@ static inline void nm_pack_launch(NmParcsr& M, NmPack& P, const double* x, const
   NmCtx& c = nm_ctx();
   NmPackArgs A;
   A.blob = P.blob.p; A.desc = P.desc.p; A.nchunk = P.nchunk; A.chunks_per_cta = P.chunks_per_cta;
-  A.x = x; A.xg = M.halo.xg.p ? M.halo.xg.p : x; A.ncol = M.ncol;
+  A.x = x; A.xg = M.halo.xg_cur ? M.halo.xg_cur : x; A.ncol = M.ncol;
   A.stage_bytes = P.stage_bytes; A.xs_doubles = P.xs_doubles; A.nstage = P.nstage;
   static const int dbg = getenv("NM_PACK_DBG") ? atoi(getenv("NM_PACK_DBG")) : 0;
   A.dbg = dbg;

@@ -21,9 +21,10 @@ def _selftest(S, R, x, ncolb=None):
     return y, order, dict(zip(("nchunk", "grid", "threads", "smem", "nstage", "maxper", "padded", "sum_nd"), info.tolist()))
 
 
-CONFIGS = [dict(), dict(NM_SLAB_THREADS="64"), dict(NM_SLAB_THREADS="256", NM_SLAB_STAGES="3"),
+CONFIGS = [dict(), dict(NM_SLAB_THREADS="64"), dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="8"),
+           dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="3", NM_SLAB_MAXGRID="2"), dict(NM_SLAB_THREADS="128", NM_SLAB_SPLIT="32"), dict(NM_SLAB_THREADS="256", NM_SLAB_STAGES="3"),
            dict(NM_SLAB_ENTRIES="200", NM_SLAB_DISTINCT="90", NM_SLAB_MAXGRID="2"),
-           dict(NM_SLAB_THREADS="64", NM_SLAB_ENTRIES="96", NM_SLAB_DISTINCT="40", NM_SLAB_MAXGRID="1", NM_SLAB_STAGES="1"),
+           dict(NM_SLAB_THREADS="64", NM_SLAB_ENTRIES="96", NM_SLAB_DISTINCT="40", NM_SLAB_MAXGRID="1", NM_SLAB_STAGES="2"),
            dict(NM_PACK_ORDER="0", NM_PACK_BANK_AWARE="0"), dict(NM_SLAB_SPLIT="8"),
            dict(NM_SLAB_SPLIT="4", NM_SLAB_THREADS="64", NM_SLAB_MAXGRID="3")]
 
@@ -54,7 +55,7 @@ def test_slab_pack_walk_equals_csr_product(monkeypatch, cfg):
         nnz = S.nnz
         assert info["padded"] >= nnz
         if not cfg:
-            assert info["padded"] <= 1.25 * nnz, info         # padding stays small with length-sorted slices
+            assert info["padded"] <= 1.5 * nnz, info          # padding stays bounded (warps hold lanes of similar length)
 
 
 def test_slab_pack_with_ghost_columns(monkeypatch):
