@@ -62,6 +62,8 @@ int nm_chebiter_stats(void* cheb, long long* nsolve, long long* nmatvec, int* de
 /* kind: 0 plain kernels, 1 TMA-staged packed kernel, 2 sliced JDS, 3 warp-sliced ELL slabs (k_slab);
    bytes: matrix bytes one step streams */
 int nm_chebiter_pack_info(void* cheb, int* kind, long long* bytes);
+/* diagnostic (NM_SLAB_TRACE=1): per CTA and chunk 8 clock64 stamps of the last k_slab launch, [grid][64][8] */
+int nm_chebiter_trace_dump(void* cheb, long long* out, long long cap, int* grid, int* cta_first /* grid+1 */);
 /* host-only self-test of the slab packer (no GPU): packs the pattern, walks the blobs as k_slab does and returns
    y = A x in pack order, the pack order and {nchunk, grid, threads, smem_bytes, nstage, max_chunks_per_cta, padded} */
 int nm_slab_host_selftest(int n, int ncolb, int R, const int* rp, const int* idx, const double* vals, const double* x,

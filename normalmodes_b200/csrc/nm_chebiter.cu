@@ -169,6 +169,17 @@ extern "C" int nm_chebiter_pack_info(void* h, int* kind, long long* bytes) {
   if (bytes) *bytes = k == 3 ? C.pslab.bytes : (k == 2 ? C.psell.bytes : (k == 1 ? C.ppack.bytes : C.M->fmt_bytes));
   NM_API_END
 }
+// diagnostic (NM_SLAB_TRACE=1): clock64 stamps of the last k_slab launch, [grid][64 chunks][8 stamps]; returns grid
+extern "C" int nm_chebiter_trace_dump(void* h, long long* out, long long cap, int* grid, int* cta_first) {
+  NM_API_BEGIN
+  NmChebIter& C = *(NmChebIter*)h;
+  NM_REQUIRE(C.pslab.trace.n > 0, "no trace (set NM_SLAB_TRACE=1 before creating the ChebIter)");
+  NM_REQUIRE(cap >= (long long)C.pslab.trace.n, "trace buffer too small");
+  C.pslab.trace.download(out, C.pslab.trace.n);
+  if (grid) *grid = C.pslab.grid;
+  if (cta_first) C.pslab.cta_first.download(cta_first, C.pslab.grid + 1);
+  NM_API_END
+}
 extern "C" int nm_chebiter_stats(void* h, long long* nsolve, long long* nmatvec, int* deg, double* lmin, double* lmax) {
   NM_API_BEGIN
   NmChebIter& C = *(NmChebIter*)h;

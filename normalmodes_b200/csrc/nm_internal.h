@@ -196,6 +196,7 @@ struct NmSlab {
   long long bytes = 0;                    // blob bytes = what one product streams
   long long entries = 0, padded_entries = 0;
   DBuf<int> order;                        // pack position -> caller's index row
+  DBuf<long long> trace;                  // NM_SLAB_TRACE=1: grid x 64 x 8 clock stamps of the last launch
 };
 
 struct NmParcsr {

@@ -26,7 +26,9 @@ struct NmSlabArgs {
   const double* xg;
   int ncol;                 // owned scalar columns (gather ids >= ncol come from xg)
   int stage_bytes, xs_doubles, nstage;
+  long long* trace;         // NM_SLAB_TRACE: per CTA and chunk 8 clock64 stamps of thread 0 (diagnostic), else null
 };
+#define NM_SLAB_STAMP(p) do { if (A.trace && tid == 0) A.trace[((size_t)blockIdx.x * NM_SLAB_MAXDESC + it) * 8 + (p)] = clock64(); } while (0)
 
 struct NmSlabView {
   NmSlabHeader h;
@@ -86,6 +88,7 @@ __global__ void __launch_bounds__(T) k_slab(NmSlabArgs A, Epi epi) {
   auto gather = [&](int it) {
     const int s = it % A.nstage;
     nm_mbar_wait(bars + s, (uint32_t)((it / A.nstage) & 1));
+    if (A.trace && tid == 0 && it > 0) A.trace[((size_t)blockIdx.x * NM_SLAB_MAXDESC + it - 1) * 8 + 1] = clock64();
     const NmSlabView v = nm_slab_view(stage0 + (size_t)s * A.stage_bytes);
     double* xs = xs0 + (size_t)(it & 1) * A.xs_doubles;
     const int tot = R * v.h.nd;
@@ -101,7 +104,9 @@ __global__ void __launch_bounds__(T) k_slab(NmSlabArgs A, Epi epi) {
   for (int it = 0; it < nmine; ++it) {
     const NmSlabView v = nm_slab_view(stage0 + (size_t)(it % A.nstage) * A.stage_bytes);
     const double* xs = xs0 + (size_t)(it & 1) * A.xs_doubles;
+    NM_SLAB_STAMP(0);
     if (it + 1 < nmine) gather(it + 1);
+    NM_SLAB_STAMP(2);
     const bool walk = warp < v.h.nslice;
     const unsigned lw = walk ? (unsigned)v.slane[tid] : 0u;
     const bool own = (lw & 0x8000u) != 0u;                       // first lane of a row: does its epilogue
@@ -114,6 +119,7 @@ __global__ void __launch_bounds__(T) k_slab(NmSlabArgs A, Epi epi) {
     double acc[R];
 #pragma unroll
     for (int c = 0; c < R; ++c) acc[c] = 0.0;
+    NM_SLAB_STAMP(3);
     if (walk) {
       const uint2 t = v.tbl[warp];
       const double* pv = v.sv + t.x + lane;
@@ -127,6 +133,7 @@ __global__ void __launch_bounds__(T) k_slab(NmSlabArgs A, Epi epi) {
         for (int c = 0; c < R; ++c) acc[c] += m * xp[c];
       }
     }
+    NM_SLAB_STAMP(4);
     // rows shared by several adjacent lanes of the warp: fixed-order segmented tree sum into the row's first lane
     for (int s = 0; (1 << s) < v.h.gmax; ++s) {
 #pragma unroll
@@ -139,8 +146,11 @@ __global__ void __launch_bounds__(T) k_slab(NmSlabArgs A, Epi epi) {
 #pragma unroll
       for (int c = 0; c < R; ++c) epi.apply(row0 + c, acc[c], in[c]);
     }
+    NM_SLAB_STAMP(5);
     nm_cp_async_wait_all();
+    NM_SLAB_STAMP(6);
     __syncthreads();             // blob it and xs[it&1] consumed by every warp; xs of chunk it+1 complete
+    NM_SLAB_STAMP(7);
     if (tid == 0 && it + A.nstage < nmine) issue(it + A.nstage);
   }
 }
@@ -152,6 +162,7 @@ static inline void nm_slab_launch_t(NmParcsr& M, NmSlab& S, const double* x, con
   A.blob = S.blob.p; A.desc = S.desc.p; A.cta_first = S.cta_first.p;
   A.x = x; A.xg = M.halo.xg_cur ? M.halo.xg_cur : x; A.ncol = M.ncol;
   A.stage_bytes = S.stage_bytes; A.xs_doubles = S.xs_doubles; A.nstage = S.nstage;
+  A.trace = S.trace.p;
   static bool attr_set = false;                                  // per template instantiation
   if (!attr_set) {
     NM_CUDA(cudaFuncSetAttribute(k_slab<R, T, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

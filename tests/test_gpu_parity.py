@@ -370,7 +370,7 @@ def test_packed_kernel_ring_and_chunking(nm, monkeypatch, sell, entries, distinc
 
 
 SLAB_CONFIGS = [dict(), dict(NM_SLAB_THREADS="64", NM_SLAB_STAGES="3"), dict(NM_SLAB_THREADS="128", NM_SLAB_SPLIT="32", NM_SLAB_STAGES="3"),
-                dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="8"), dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="3", NM_SLAB_MAXGRID="2"),
+                dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="8"), dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="4", NM_SLAB_MAXGRID="2"),
                 dict(NM_SLAB_ENTRIES="200", NM_SLAB_DISTINCT="140", NM_SLAB_MAXGRID="2"),
                 dict(NM_SLAB_THREADS="64", NM_SLAB_ENTRIES="96", NM_SLAB_DISTINCT="140", NM_SLAB_MAXGRID="1", NM_SLAB_STAGES="2"),
                 dict(NM_SLAB_SPLIT="4", NM_SLAB_MAXGRID="3", NM_SLAB_STAGES="4"), dict(NM_CHEB_KERNEL="pack"),

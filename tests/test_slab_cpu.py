@@ -22,7 +22,7 @@ def _selftest(S, R, x, ncolb=None):
 
 
 CONFIGS = [dict(), dict(NM_SLAB_THREADS="64"), dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="8"),
-           dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="3", NM_SLAB_MAXGRID="2"), dict(NM_SLAB_THREADS="128", NM_SLAB_SPLIT="32"), dict(NM_SLAB_THREADS="256", NM_SLAB_STAGES="3"),
+           dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="4", NM_SLAB_MAXGRID="2"), dict(NM_SLAB_THREADS="128", NM_SLAB_SPLIT="32"), dict(NM_SLAB_THREADS="256", NM_SLAB_STAGES="3"),
            dict(NM_SLAB_ENTRIES="200", NM_SLAB_DISTINCT="90", NM_SLAB_MAXGRID="2"),
            dict(NM_SLAB_THREADS="64", NM_SLAB_ENTRIES="96", NM_SLAB_DISTINCT="40", NM_SLAB_MAXGRID="1", NM_SLAB_STAGES="2"),
            dict(NM_PACK_ORDER="0", NM_PACK_BANK_AWARE="0"), dict(NM_SLAB_SPLIT="8"),
