@@ -323,7 +323,7 @@ def main():
     infoB = mvmod.parcsr_info(mv.sBV)
     kind = C.c_int(); pbytes = C.c_longlong()
     _lib.check(L.nm_chebiter_pack_info(mv.chebB, C.byref(kind), C.byref(pbytes)))
-    kname = ("k_spmv_kron3<EpiCheb>", "k_pack<KRON3,EpiCheb>", "k_sell<KRON3,EpiCheb>")[kind.value]
+    kname = ("k_spmv_kron3<EpiCheb>", "k_pack<KRON3,EpiCheb>", "k_sell<KRON3,EpiCheb>", "k_slab<3,EpiCheb>")[kind.value]
     bytes_launch = cheb_step_bytes(infoB["nnz"], infoB["nrow"])
     fmt_bytes_launch = pbytes.value + 48 * infoB["nrow"]
     achieved = bytes_launch / (us_launch * 1e-6) / 1e9
@@ -331,10 +331,28 @@ def main():
                     achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None, peak_source=peak_src,
                     us_per_launch=us_launch, algorithmic_bytes_per_launch=bytes_launch,
                     format_bytes_per_launch=fmt_bytes_launch, format_gbs=fmt_bytes_launch / (us_launch * 1e-6) / 1e9)
+    comm = None
+    if use_dist:
+        mode = C.c_int(); ng = C.c_int(); ns = C.c_int()
+        _lib.check(L.nm_parcsr_halo_info(mv.sBV, C.byref(mode), C.byref(ng), C.byref(ns)))
+        for _ in range(5):
+            _lib.check(L.nm_parcsr_halo_exchange_dev(mv.sBV, C.c_void_p(z.data_ptr())))
+        barrier()
+        e0.record(stream)
+        for _ in range(200):
+            _lib.check(L.nm_parcsr_halo_exchange_dev(mv.sBV, C.c_void_p(z.data_ptr())))
+        e1.record(stream)
+        barrier()
+        comm = dict(halo=("none", "nccl send/recv", "nvlink peer window (direct stores + flags)")[mode.value],
+                    us_per_exchange=e0.elapsed_time(e1) * 1e3 / 200, ghosts_rank0=ng.value, sends_rank0=ns.value,
+                    exchanges_per_filter_degree=mv.degB + (degAp + 3 if fem.fluidcase else 1))
+        log("halo exchange alone: %.1f us (%s), %d ghosts on rank 0" % (comm["us_per_exchange"], comm["halo"], ng.value))
     out = dict(metric="filtered_spmv_hbm_gbs", value=value, unit="GB/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
                ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
                data="synthetic", config=config, clocks=cs.summary(), e2e=e2e, gpu_launches=launches, roofline=roofline,
                setup_s=dict(assembly=t_asm, setupmatvec=t_setup, bounds=t_bounds))
+    if comm:
+        out["comm"] = comm
     if a.solve:
         t0 = time.time()
         r = pevsl.pnm_apply_pevsl(mv, a.lowfreq, a.upfreq, recheck=False)

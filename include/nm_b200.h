@@ -48,6 +48,10 @@ int nm_parcsr_info(void* mat, int* nrow, int* ncol, long long* nnz, int* format,
  * d_i = 1/sqrt(sign*M_ii), M~_ij = (sign*M_ij*d_j)*d_i ; d_host[n_local] receives d (may be NULL). */
 int nm_parcsr_jacobi_scale(void* mat, double sign, double* d_host);
 int nm_parcsr_get_values(void* mat, double* a_host /* nnz_local */);
+/* the halo (ghost-DOF) exchange of one product alone, on device vectors; mode: 0 none, 1 NCCL send/recv, 2 NVLink peer
+   window (direct peer stores + arrival flags) */
+int nm_parcsr_halo_exchange_dev(void* mat, const double* x_dev);
+int nm_parcsr_halo_info(void* mat, int* mode, int* nghost, int* nsend);
 /* host-only (no GPU, no communicator): receive side of one rank's halo plan -- sorted ghost column ids (ghost_glob may
    be null) and the number owned by each rank; the device plan of nm_parcsr_create is built from the same routine */
 int nm_halo_plan_host(int nranks, int rank, const int* col_starts, long long nnz, const int* ja, int* nghost,

@@ -34,10 +34,12 @@ __global__ void k_halo_push(NmPushArgs A, const double* __restrict__ x, const in
     while (i >= A.send_off[r + 1]) ++r;
     A.peer_xg[r][i - A.send_off[r]] = x[idx[i]];
   }
-  __threadfence_system();
   __shared__ int last;
-  __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(A.ctr, 1u) == gridDim.x - 1);
+  __syncthreads();                           // the block's stores happen-before thread 0's fence (cumulative)
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last = (atomicAdd(A.ctr, 1u) == gridDim.x - 1);
+  }
   __syncthreads();
   if (!last) return;
   __threadfence_system();                    // every block's stores are ordered before the flags below
@@ -83,8 +85,8 @@ void nm_halo_exchange(NmParcsr& M, const double* x, const int* send_idx) {
     }
     A.my_flag = (const unsigned long long*)(c.win + h.win_flag);
     A.epoch = epoch; A.ctr = c.push_ctr; A.status = c.dev_status;
-    const int blocks = std::max(1, std::min(32, nm_div_up(h.nsend, 256)));
-    k_halo_push<<<blocks, 256, 0, c.stream>>>(A, x, send_idx ? send_idx : h.send_idx.p);
+    const int blocks = std::max(1, std::min(16, nm_div_up(h.nsend, 2048)));
+    k_halo_push<<<blocks, 512, 0, c.stream>>>(A, x, send_idx ? send_idx : h.send_idx.p);
     c.launches++;
     h.xg_cur = (double*)(c.win + h.win_xg[par]);
     return;
@@ -503,6 +505,21 @@ extern "C" int nm_parcsr_matvec_dev(void* h, const double* x_dev, double* y_dev)
   NM_API_END
 }
 
+// halo exchange alone (device vector of the owned columns), asynchronous on nm_stream(): timing / diagnostics
+extern "C" int nm_parcsr_halo_exchange_dev(void* h, const double* x_dev) {
+  NM_API_BEGIN
+  nm_halo_exchange(*(NmParcsr*)h, x_dev);
+  NM_API_END
+}
+// mode: 0 single rank / no halo, 1 NCCL send/recv, 2 NVLink peer window (direct peer stores + arrival flags)
+extern "C" int nm_parcsr_halo_info(void* h, int* mode, int* nghost, int* nsend) {
+  NM_API_BEGIN
+  NmParcsr& M = *(NmParcsr*)h;
+  if (mode) *mode = nm_ctx().nranks == 1 ? 0 : (M.halo.p2p ? 2 : 1);
+  if (nghost) *nghost = M.halo.nghost;
+  if (nsend) *nsend = M.halo.nsend;
+  NM_API_END
+}
 extern "C" int nm_parcsr_info(void* h, int* nrow, int* ncol, long long* nnz, int* format, int* nghost,
                               long long* fmt_bytes) {
   NM_API_BEGIN
