@@ -327,8 +327,15 @@ def main():
     bytes_launch = cheb_step_bytes(infoB["nnz"], infoB["nrow"])
     fmt_bytes_launch = pbytes.value + 48 * infoB["nrow"]
     achieved = bytes_launch / (us_launch * 1e-6) / 1e9
+    traffic = None                      # dram bytes per launch of this kernel from the committed ncu --set full capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if kind.value == 3 and nr == 1 and tj.get("n_rows") == infoB["nrow"]:
+            traffic = tj["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = dict(bound="hbm", kernel="%s (fused ChebIter step on B~, %s; us_per_launch includes the 2 permute kernels of a solve spread over degB launches)" % (kname, infoB["format"]),
-                    achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None, peak_source=peak_src,
+                    achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, peak_source=peak_src,
                     us_per_launch=us_launch, algorithmic_bytes_per_launch=bytes_launch,
                     format_bytes_per_launch=fmt_bytes_launch, format_gbs=fmt_bytes_launch / (us_launch * 1e-6) / 1e9)
     comm = None

@@ -193,6 +193,8 @@ struct NmSlab {
   int nchunk = 0;                         // 0: not built
   int grid = 0, threads = 0, max_chunks_per_cta = 0;
   int stage_bytes = 0, xs_doubles = 0, nstage = 0, smem_bytes = 0;
+  bool ws = false;                        // warp-specialised kernel (k_slabws): nprod producer warps, nxs x buffers
+  int nxs = 2, nprod = 0;
   long long bytes = 0;                    // blob bytes = what one product streams
   long long entries = 0, padded_entries = 0;
   DBuf<int> order;                        // pack position -> caller's index row

@@ -27,6 +27,7 @@ struct NmSlabHost {
   std::vector<int> cta_first, slot_src, order;
   std::vector<unsigned> slot_off8;
   int nchunk = 0, grid = 0, threads = 0, max_chunks_per_cta = 0, stage_bytes = 0, xs_doubles = 0, nstage = 0, smem_bytes = 0;
+  int ws = 0, nxs = 2, nprod = 0;
   long long padded_entries = 0;
 };
 
@@ -281,11 +282,20 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
   H.threads = T;
   H.xs_doubles = R * max_nd;
   H.stage_bytes = (int)up16(max_blob);
-  H.nstage = std::max(2, std::min(8, nm_env_int("NM_SLAB_STAGES", 2)));   // >= 2: blob it+1 is awaited while chunk it is walked
-  const int fixed = NM_SLAB_MAXDESC * (int)sizeof(NmPackDesc) + 64 + 16 * H.xs_doubles;
+  // NM_SLAB_WS (default 1): warp-specialised kernel -- producer warps + full/empty mbarriers, deeper rings
+  H.ws = nm_env_int("NM_SLAB_WS", 1) != 0;
+  H.nprod = std::max(1, std::min(4, nm_env_int("NM_SLAB_PRODUCERS", 2)));
+  H.nstage = std::max(2, std::min(8, nm_env_int("NM_SLAB_STAGES", H.ws ? 3 : 2)));   // >= 2: blob it+1 is awaited while chunk it is walked
+  H.nxs = H.ws ? std::max(2, std::min(8, nm_env_int("NM_SLAB_XS", 3))) : 2;
   const int budget = 226 * 1024;
-  while (H.nstage > 2 && (int)up16(fixed) + H.nstage * H.stage_bytes > budget) H.nstage--;
-  H.smem_bytes = (int)up16(fixed) + H.nstage * H.stage_bytes;
+  auto smem_of = [&]() {
+    const int fixed = NM_SLAB_MAXDESC * (int)sizeof(NmPackDesc) + (H.ws ? 256 : 64) + 8 * H.nxs * H.xs_doubles;
+    return (int)up16(fixed) + H.nstage * H.stage_bytes;
+  };
+  while (smem_of() > budget && (H.nstage > 2 || H.nxs > 2)) {
+    if (H.nxs > 2 && H.nxs >= H.nstage) H.nxs--; else if (H.nstage > 2) H.nstage--; else H.nxs--;
+  }
+  H.smem_bytes = smem_of();
   if (H.smem_bytes > budget) return false;
   const int fit = std::max(1, (228 * 1024) / (H.smem_bytes + 1024));          // 1 KB reserved per CTA
   const int per_sm = std::max(1, std::min(fit, nm_env_int("NM_SLAB_CTAS_PER_SM", fit)));
@@ -334,6 +344,7 @@ void nm_slab_build_into(NmParcsr& M, NmSlab& S, const std::vector<int>& rp, cons
   if (!slab_build_host(H, rp, idx, n, R, ncolb, nm_ctx().sm_count)) return;
   S.threads = H.threads; S.xs_doubles = H.xs_doubles; S.stage_bytes = H.stage_bytes; S.nstage = H.nstage;
   S.smem_bytes = H.smem_bytes; S.grid = H.grid; S.max_chunks_per_cta = H.max_chunks_per_cta;
+  S.ws = H.ws != 0; S.nxs = H.nxs; S.nprod = H.nprod;
   S.bytes = (long long)H.blob.size();
   S.entries = (long long)H.slot_src.size(); S.padded_entries = H.padded_entries;
   S.nslot = (long long)H.slot_src.size();

@@ -155,6 +155,177 @@ __global__ void __launch_bounds__(T) k_slab(NmSlabArgs A, Epi epi) {
   }
 }
 
+// ---------------------------------------------------------------- warp-specialised variant
+// ncu + clock64 traces of k_slab (profiles/r1c_kslab_summary.md): the SM's load/store pipe is the busy unit (shared-
+// memory wavefronts of the walk + the x gather + the epilogue), but it idles half of the time because a CTA's
+// phases -- wait for the blob, issue the gather, walk, epilogue -- are serialised by the per-chunk __syncthreads.
+// k_slabws splits the CTA: NP producer warps keep the TMA ring full and issue the cp.async gathers of the chunks
+// AHEAD (completion tracked by mbarriers through cp.async.mbarrier.arrive), NC consumer warps only walk and run the
+// epilogue; stages and x buffers are handed over with full/empty mbarriers, no CTA-wide barrier inside the loop.
+__device__ __forceinline__ void nm_mbar_wait_bounded(uint64_t* b, uint32_t parity) {
+  uint32_t done;
+  const uint32_t a = nm_smem_u32(b);
+  const long long t0 = clock64();
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (!done && clock64() - t0 > 4000000000ll) __trap();       // ~2 s: a lost arrival must not hang the GPU
+  } while (!done);
+}
+__device__ __forceinline__ void nm_mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(nm_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void nm_cp_async_mbar_arrive_noinc(uint64_t* b) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(nm_smem_u32(b)) : "memory");
+}
+
+struct NmSlabWsArgs {
+  NmSlabArgs a;
+  int nxs;                  // x buffers in the ring
+  int np;                   // producer warps
+};
+
+template <int R, int NC, class Epi>
+__global__ void __launch_bounds__(32 * (NC + 4)) k_slabws(NmSlabWsArgs W, Epi epi) {
+  const NmSlabArgs& A = W.a;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c0 = A.cta_first[blockIdx.x];
+  const int nmine = A.cta_first[blockIdx.x + 1] - c0;
+  if (nmine <= 0) return;
+  const int S = A.nstage, X = W.nxs, NP = W.np;
+  // shared layout: [descs][full_blob 8][empty_blob 8][full_xs 8][empty_xs 8][xs x X][stages x S]
+  NmPackDesc* sdesc = (NmPackDesc*)smem;
+  uint64_t* full_blob = (uint64_t*)(smem + NM_SLAB_MAXDESC * sizeof(NmPackDesc));
+  uint64_t* empty_blob = full_blob + 8;
+  uint64_t* full_xs = full_blob + 16;
+  uint64_t* empty_xs = full_blob + 24;
+  double* xs0 = (double*)(full_blob + 32);
+  unsigned char* stage0 =
+      smem + ((NM_SLAB_MAXDESC * sizeof(NmPackDesc) + 256 + 8 * (size_t)X * A.xs_doubles + 15) & ~(size_t)15);
+  for (int i = tid; i < nmine; i += blockDim.x) sdesc[i] = A.desc[c0 + i];
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { nm_mbar_init(full_blob + s, 1); nm_mbar_init(empty_blob + s, NC); }
+    for (int x = 0; x < X; ++x) { nm_mbar_init(full_xs + x, 32 * NP); nm_mbar_init(empty_xs + x, NC); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp >= NC) {
+    // ================================================= producers
+    const int pw = warp - NC;                                   // producer warp index
+    const int ptid = pw * 32 + lane, pthreads = 32 * NP;
+    uint64_t policy = 0;
+    auto issue = [&](int j) {
+      const NmPackDesc d = sdesc[j];
+      const int s = j % S;
+      nm_mbar_expect_tx(full_blob + s, d.bytes);
+      nm_bulk_g2s(stage0 + (size_t)s * A.stage_bytes, A.blob + 16ull * d.off16, d.bytes, full_blob + s, policy);
+    };
+    if (ptid == 0) {
+      policy = nm_policy_evict_first();
+      for (int j = 0; j < min(S, nmine); ++j) issue(j);
+    }
+    const double* __restrict__ x = A.x;
+    const double* __restrict__ xg = A.xg;
+    const int ncol = A.ncol;
+    for (int it = 0; it < nmine; ++it) {
+      // a. x values of chunk it -> xs[it % X] (free once the consumers are done with chunk it - X)
+      const int s = it % S, xb = it % X;
+      nm_mbar_wait_bounded(full_blob + s, (uint32_t)((it / S) & 1));
+      if (it >= X) nm_mbar_wait_bounded(empty_xs + xb, (uint32_t)(((it / X) - 1) & 1));
+      const NmSlabView v = nm_slab_view(stage0 + (size_t)s * A.stage_bytes);
+      double* xs = xs0 + (size_t)xb * A.xs_doubles;
+      const int tot = R * v.h.nd;
+      for (int j = ptid; j < tot; j += pthreads) {
+        const int node = (R == 1) ? j : j / 3;
+        const int c = R * v.scols[node] + (j - R * node);
+        nm_cp_async8(xs + j, c < ncol ? x + c : xg + (c - ncol));
+      }
+      nm_cp_async_mbar_arrive_noinc(full_xs + xb);
+      // b. refill the stage of chunk it-1 (consumed once all NC warps released it) with chunk it-1+S
+      if (ptid == 0 && it >= 1) {
+        const int j = it - 1 + S;
+        if (j < nmine) {
+          nm_mbar_wait_bounded(empty_blob + (j % S), (uint32_t)(((j / S) - 1) & 1));
+          issue(j);
+        }
+      }
+      __syncwarp();
+    }
+    return;
+  }
+  // =================================================== consumers
+  for (int it = 0; it < nmine; ++it) {
+    const int s = it % S, xb = it % X;
+    nm_mbar_wait_bounded(full_blob + s, (uint32_t)((it / S) & 1));
+    const NmSlabView v = nm_slab_view(stage0 + (size_t)s * A.stage_bytes);
+    const double* xs = xs0 + (size_t)xb * A.xs_doubles;
+    const bool walk = warp < v.h.nslice;
+    const unsigned lw = walk ? (unsigned)v.slane[tid] : 0u;
+    const bool own = (lw & 0x8000u) != 0u;                       // first lane of a row: does its epilogue
+    const int row0 = R * (v.h.first + (int)(lw & 0x3ffu));
+    typename Epi::In in[R];
+    if (own) {
+#pragma unroll
+      for (int c = 0; c < R; ++c) in[c] = epi.load(row0 + c);
+    }
+    double acc[R];
+#pragma unroll
+    for (int c = 0; c < R; ++c) acc[c] = 0.0;
+    uint2 t = make_uint2(0u, 0u);
+    if (walk) t = v.tbl[warp];
+    nm_mbar_wait_bounded(full_xs + xb, (uint32_t)((it / X) & 1));
+    if (walk) {
+      const double* pv = v.sv + t.x + lane;
+      const unsigned short* pi = v.sidx + t.x + lane;
+      const int w = (int)t.y;
+#pragma unroll 4
+      for (int k = 0; k < w; ++k) {
+        const double m = pv[32 * k];
+        const double* xp = xs + R * (int)pi[32 * k];
+#pragma unroll
+        for (int c = 0; c < R; ++c) acc[c] += m * xp[c];
+      }
+    }
+    const int gmax = v.h.gmax;
+    __syncwarp();
+    if (lane == 0) { nm_mbar_arrive(empty_blob + s); nm_mbar_arrive(empty_xs + xb); }   // blob and x buffer consumed
+    for (int q = 0; (1 << q) < gmax; ++q) {
+#pragma unroll
+      for (int c = 0; c < R; ++c) {
+        const double other = __shfl_down_sync(0xffffffffu, acc[c], 1 << q);
+        if (lw & (1u << (10 + q))) acc[c] += other;
+      }
+    }
+    if (own) {
+#pragma unroll
+      for (int c = 0; c < R; ++c) epi.apply(row0 + c, acc[c], in[c]);
+    }
+  }
+}
+
+template <int R, int NC, class Epi>
+static inline void nm_slabws_launch_t(NmParcsr& M, NmSlab& S, const double* x, const Epi& epi) {
+  NmCtx& c = nm_ctx();
+  NmSlabWsArgs W;
+  NmSlabArgs& A = W.a;
+  A.blob = S.blob.p; A.desc = S.desc.p; A.cta_first = S.cta_first.p;
+  A.x = x; A.xg = M.halo.xg_cur ? M.halo.xg_cur : x; A.ncol = M.ncol;
+  A.stage_bytes = S.stage_bytes; A.xs_doubles = S.xs_doubles; A.nstage = S.nstage;
+  A.trace = nullptr;
+  W.nxs = S.nxs; W.np = S.nprod;
+  static bool attr_set = false;                                  // per template instantiation
+  if (!attr_set) {
+    NM_CUDA(cudaFuncSetAttribute(k_slabws<R, NC, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  k_slabws<R, NC, Epi><<<S.grid, 32 * (NC + S.nprod), S.smem_bytes, c.stream>>>(W, epi);
+  c.launches++;
+}
+
 template <int R, int T, class Epi>
 static inline void nm_slab_launch_t(NmParcsr& M, NmSlab& S, const double* x, const Epi& epi) {
   NmCtx& c = nm_ctx();
@@ -177,6 +348,18 @@ template <class Epi>
 static inline void nm_spmv_slab_epi(NmParcsr& M, NmSlab& S, const double* x, const Epi& epi, const int* send_idx) {
   nm_halo_exchange(M, x, send_idx);
   const bool blk = M.format == NM_FMT_KRON3;
+  if (S.ws) {
+    if (S.threads == 512) {
+      if (blk) nm_slabws_launch_t<3, 16, Epi>(M, S, x, epi); else nm_slabws_launch_t<1, 16, Epi>(M, S, x, epi);
+    } else if (S.threads == 256) {
+      if (blk) nm_slabws_launch_t<3, 8, Epi>(M, S, x, epi); else nm_slabws_launch_t<1, 8, Epi>(M, S, x, epi);
+    } else if (S.threads == 64) {
+      if (blk) nm_slabws_launch_t<3, 2, Epi>(M, S, x, epi); else nm_slabws_launch_t<1, 2, Epi>(M, S, x, epi);
+    } else {
+      if (blk) nm_slabws_launch_t<3, 4, Epi>(M, S, x, epi); else nm_slabws_launch_t<1, 4, Epi>(M, S, x, epi);
+    }
+    return;
+  }
   if (S.threads == 512) {
     if (blk) nm_slab_launch_t<3, 512, Epi>(M, S, x, epi); else nm_slab_launch_t<1, 512, Epi>(M, S, x, epi);
   } else if (S.threads == 256) {

@@ -369,17 +369,23 @@ def test_packed_kernel_ring_and_chunking(nm, monkeypatch, sell, entries, distinc
     nm.nm_parcsr_free(h)
 
 
-SLAB_CONFIGS = [dict(), dict(NM_SLAB_THREADS="64", NM_SLAB_STAGES="3"), dict(NM_SLAB_THREADS="128", NM_SLAB_SPLIT="32", NM_SLAB_STAGES="3"),
-                dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="8"), dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="4", NM_SLAB_MAXGRID="2"),
+SLAB_CONFIGS = [dict(), dict(NM_SLAB_WS="0"), dict(NM_SLAB_THREADS="64", NM_SLAB_STAGES="3"),
+                dict(NM_SLAB_THREADS="128", NM_SLAB_SPLIT="32", NM_SLAB_STAGES="4", NM_SLAB_XS="2", NM_SLAB_PRODUCERS="1"),
+                dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="8", NM_SLAB_PRODUCERS="4"),
+                dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="4", NM_SLAB_MAXGRID="2"),
+                dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="4", NM_SLAB_MAXGRID="2", NM_SLAB_WS="0"),
                 dict(NM_SLAB_ENTRIES="200", NM_SLAB_DISTINCT="140", NM_SLAB_MAXGRID="2"),
-                dict(NM_SLAB_THREADS="64", NM_SLAB_ENTRIES="96", NM_SLAB_DISTINCT="140", NM_SLAB_MAXGRID="1", NM_SLAB_STAGES="2"),
-                dict(NM_SLAB_SPLIT="4", NM_SLAB_MAXGRID="3", NM_SLAB_STAGES="4"), dict(NM_CHEB_KERNEL="pack"),
+                dict(NM_SLAB_ENTRIES="200", NM_SLAB_DISTINCT="140", NM_SLAB_MAXGRID="2", NM_SLAB_WS="0"),
+                dict(NM_SLAB_THREADS="64", NM_SLAB_ENTRIES="96", NM_SLAB_DISTINCT="140", NM_SLAB_MAXGRID="1", NM_SLAB_STAGES="2", NM_SLAB_XS="2"),
+                dict(NM_SLAB_THREADS="64", NM_SLAB_ENTRIES="96", NM_SLAB_DISTINCT="140", NM_SLAB_MAXGRID="1", NM_SLAB_STAGES="5", NM_SLAB_XS="4"),
+                dict(NM_SLAB_SPLIT="4", NM_SLAB_MAXGRID="3", NM_SLAB_STAGES="4", NM_SLAB_WS="0"), dict(NM_CHEB_KERNEL="pack"),
                 dict(NM_CHEB_KERNEL="sell")]
 
 
 @pytest.mark.parametrize("cfg", SLAB_CONFIGS)
 def test_chebiter_slab_kernel_configs(nm, monkeypatch, cfg):
-    """Fused Chebyshev step through k_slab (TMA ring, cp.async x staging, thread-per-row walk, split rows) on the
+    """Fused Chebyshev step through k_slabws / k_slab (TMA ring, cp.async x staging, thread-per-row walk, split rows,
+    warp-specialised producers with full/empty mbarriers) on the
     KRON3 B~ (P1 and P2) and the CSR Ap~, with chunk sizes / grid limits that force many chunks per CTA (ring
     wrap-around, mbarrier phase flips), against the oracle's Chebyshev iteration; k_pack / k_sell stay covered."""
     from oracle import fem, solver
