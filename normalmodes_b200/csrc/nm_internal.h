@@ -195,6 +195,7 @@ struct NmSlab {
   int stage_bytes = 0, xs_doubles = 0, nstage = 0, smem_bytes = 0;
   bool ws = false;                        // warp-specialised kernel (k_slabws): nprod producer warps, nxs x buffers
   int nxs = 2, nprod = 0;
+  bool pdl = true;                        // programmatic dependent launch of consecutive steps (NM_SLAB_PDL)
   long long bytes = 0;                    // blob bytes = what one product streams
   long long entries = 0, padded_entries = 0;
   DBuf<int> order;                        // pack position -> caller's index row

@@ -284,9 +284,9 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
   H.stage_bytes = (int)up16(max_blob);
   // NM_SLAB_WS (default 1): warp-specialised kernel -- producer warps + full/empty mbarriers, deeper rings
   H.ws = nm_env_int("NM_SLAB_WS", 1) != 0;
-  H.nprod = std::max(1, std::min(4, nm_env_int("NM_SLAB_PRODUCERS", 2)));
-  H.nstage = std::max(2, std::min(8, nm_env_int("NM_SLAB_STAGES", H.ws ? 3 : 2)));   // >= 2: blob it+1 is awaited while chunk it is walked
-  H.nxs = H.ws ? std::max(2, std::min(8, nm_env_int("NM_SLAB_XS", 3))) : 2;
+  H.nprod = std::max(1, std::min(8, nm_env_int("NM_SLAB_PRODUCERS", 4)));
+  H.nstage = std::max(2, std::min(8, nm_env_int("NM_SLAB_STAGES", 2)));   // >= 2: blob it+1 is awaited while chunk it is walked
+  H.nxs = H.ws ? std::max(2, std::min(8, nm_env_int("NM_SLAB_XS", 2))) : 2;
   const int budget = 226 * 1024;
   auto smem_of = [&]() {
     const int fixed = NM_SLAB_MAXDESC * (int)sizeof(NmPackDesc) + (H.ws ? 256 : 64) + 8 * H.nxs * H.xs_doubles;
@@ -345,6 +345,7 @@ void nm_slab_build_into(NmParcsr& M, NmSlab& S, const std::vector<int>& rp, cons
   S.threads = H.threads; S.xs_doubles = H.xs_doubles; S.stage_bytes = H.stage_bytes; S.nstage = H.nstage;
   S.smem_bytes = H.smem_bytes; S.grid = H.grid; S.max_chunks_per_cta = H.max_chunks_per_cta;
   S.ws = H.ws != 0; S.nxs = H.nxs; S.nprod = H.nprod;
+  S.pdl = nm_env_int("NM_SLAB_PDL", 1) != 0;
   S.bytes = (long long)H.blob.size();
   S.entries = (long long)H.slot_src.size(); S.padded_entries = H.padded_entries;
   S.nslot = (long long)H.slot_src.size();

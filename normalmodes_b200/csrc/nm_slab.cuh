@@ -51,6 +51,33 @@ __device__ __forceinline__ NmSlabView nm_slab_view(const unsigned char* st) {
   return v;
 }
 
+// Asynchronous gather of a chunk's distinct x values (8 bytes per scalar component) into xs, by `nthreads` threads;
+// 4 independent column-id loads / address computations / cp.async per round so the issue latency chain overlaps.
+template <int R>
+__device__ __forceinline__ void nm_slab_gather(const NmSlabView& v, double* xs, const double* __restrict__ x,
+                                               const double* __restrict__ xg, int ncol, int t, int nthreads) {
+  const int tot = R * v.h.nd;
+  int j = t;
+  for (; j + 3 * nthreads < tot; j += 4 * nthreads) {
+    int node[4], cid[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int jj = j + u * nthreads; node[u] = (R == 1) ? jj : jj / 3; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) cid[u] = v.scols[node[u]];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int jj = j + u * nthreads;
+      const int c = R * cid[u] + (jj - R * node[u]);
+      nm_cp_async8(xs + jj, c < ncol ? x + c : xg + (c - ncol));
+    }
+  }
+  for (; j < tot; j += nthreads) {
+    const int node = (R == 1) ? j : j / 3;
+    const int c = R * v.scols[node] + (j - R * node);
+    nm_cp_async8(xs + j, c < ncol ? x + c : xg + (c - ncol));
+  }
+}
+
 template <int R, int T, class Epi>
 __global__ void __launch_bounds__(T) k_slab(NmSlabArgs A, Epi epi) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -91,12 +118,7 @@ __global__ void __launch_bounds__(T) k_slab(NmSlabArgs A, Epi epi) {
     if (A.trace && tid == 0 && it > 0) A.trace[((size_t)blockIdx.x * NM_SLAB_MAXDESC + it - 1) * 8 + 1] = clock64();
     const NmSlabView v = nm_slab_view(stage0 + (size_t)s * A.stage_bytes);
     double* xs = xs0 + (size_t)(it & 1) * A.xs_doubles;
-    const int tot = R * v.h.nd;
-    for (int j = tid; j < tot; j += T) {
-      const int node = (R == 1) ? j : j / 3;
-      const int c = R * v.scols[node] + (j - R * node);
-      nm_cp_async8(xs + j, c < ncol ? x + c : xg + (c - ncol));
-    }
+    nm_slab_gather<R>(v, xs, x, xg, ncol, tid, T);
   };
   gather(0);
   nm_cp_async_wait_all();
@@ -189,7 +211,7 @@ struct NmSlabWsArgs {
 };
 
 template <int R, int NC, class Epi>
-__global__ void __launch_bounds__(32 * (NC + 4)) k_slabws(NmSlabWsArgs W, Epi epi) {
+__global__ void __launch_bounds__(32 * (NC + 8)) k_slabws(NmSlabWsArgs W, Epi epi) {
   const NmSlabArgs& A = W.a;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -206,6 +228,9 @@ __global__ void __launch_bounds__(32 * (NC + 4)) k_slabws(NmSlabWsArgs W, Epi ep
   double* xs0 = (double*)(full_blob + 32);
   unsigned char* stage0 =
       smem + ((NM_SLAB_MAXDESC * sizeof(NmPackDesc) + 256 + 8 * (size_t)X * A.xs_doubles + 15) & ~(size_t)15);
+  // programmatic dependent launch: the NEXT step's kernel may start as SM resources free up; everything it does before
+  // its griddepcontrol.wait (descriptors, barrier init, the first TMA blob copies) touches read-only matrix data only
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (int i = tid; i < nmine; i += blockDim.x) sdesc[i] = A.desc[c0 + i];
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { nm_mbar_init(full_blob + s, 1); nm_mbar_init(empty_blob + s, NC); }
@@ -231,6 +256,7 @@ __global__ void __launch_bounds__(32 * (NC + 4)) k_slabws(NmSlabWsArgs W, Epi ep
     const double* __restrict__ x = A.x;
     const double* __restrict__ xg = A.xg;
     const int ncol = A.ncol;
+    asm volatile("griddepcontrol.wait;" ::: "memory");           // the previous step's vectors are complete and visible
     for (int it = 0; it < nmine; ++it) {
       // a. x values of chunk it -> xs[it % X] (free once the consumers are done with chunk it - X)
       const int s = it % S, xb = it % X;
@@ -238,12 +264,7 @@ __global__ void __launch_bounds__(32 * (NC + 4)) k_slabws(NmSlabWsArgs W, Epi ep
       if (it >= X) nm_mbar_wait_bounded(empty_xs + xb, (uint32_t)(((it / X) - 1) & 1));
       const NmSlabView v = nm_slab_view(stage0 + (size_t)s * A.stage_bytes);
       double* xs = xs0 + (size_t)xb * A.xs_doubles;
-      const int tot = R * v.h.nd;
-      for (int j = ptid; j < tot; j += pthreads) {
-        const int node = (R == 1) ? j : j / 3;
-        const int c = R * v.scols[node] + (j - R * node);
-        nm_cp_async8(xs + j, c < ncol ? x + c : xg + (c - ncol));
-      }
+      nm_slab_gather<R>(v, xs, x, xg, ncol, ptid, pthreads);
       nm_cp_async_mbar_arrive_noinc(full_xs + xb);
       // b. refill the stage of chunk it-1 (consumed once all NC warps released it) with chunk it-1+S
       if (ptid == 0 && it >= 1) {
@@ -258,6 +279,7 @@ __global__ void __launch_bounds__(32 * (NC + 4)) k_slabws(NmSlabWsArgs W, Epi ep
     return;
   }
   // =================================================== consumers
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   for (int it = 0; it < nmine; ++it) {
     const int s = it % S, xb = it % X;
     nm_mbar_wait_bounded(full_blob + s, (uint32_t)((it / S) & 1));
@@ -322,7 +344,14 @@ static inline void nm_slabws_launch_t(NmParcsr& M, NmSlab& S, const double* x, c
     NM_CUDA(cudaFuncSetAttribute(k_slabws<R, NC, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  k_slabws<R, NC, Epi><<<S.grid, 32 * (NC + S.nprod), S.smem_bytes, c.stream>>>(W, epi);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(S.grid); cfg.blockDim = dim3(32 * (NC + S.nprod)); cfg.dynamicSmemBytes = S.smem_bytes; cfg.stream = c.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = S.pdl ? 1 : 0;
+  NM_CUDA(cudaLaunchKernelEx(&cfg, k_slabws<R, NC, Epi>, W, epi));
   c.launches++;
 }
 

@@ -13,24 +13,21 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 KEYS = ("NM_CHEB_KERNEL", "NM_SLAB_THREADS", "NM_SLAB_STAGES", "NM_SLAB_SPLIT", "NM_SLAB_ENTRIES", "NM_SLAB_DISTINCT",
-        "NM_SLAB_CTAS_PER_SM", "NM_PACK_BANK_AWARE", "NM_PACK_ORDER", "NM_SLAB_WS", "NM_SLAB_PRODUCERS", "NM_SLAB_XS")
+        "NM_SLAB_CTAS_PER_SM", "NM_PACK_BANK_AWARE", "NM_PACK_ORDER", "NM_SLAB_WS", "NM_SLAB_PRODUCERS", "NM_SLAB_XS", "NM_SLAB_PDL")
 
 CONFIGS = [
-    dict(NM_CHEB_KERNEL="pack"),
     dict(NM_SLAB_WS="0"),
     dict(),
-    dict(NM_SLAB_PRODUCERS="1"),
-    dict(NM_SLAB_PRODUCERS="4"),
-    dict(NM_SLAB_STAGES="4", NM_SLAB_XS="3"),
-    dict(NM_SLAB_STAGES="3", NM_SLAB_XS="2"),
-    dict(NM_SLAB_STAGES="2", NM_SLAB_XS="2"),
+    dict(NM_SLAB_PDL="0"),
+    dict(NM_SLAB_PRODUCERS="2"),
+    dict(NM_SLAB_PRODUCERS="6"),
+    dict(NM_SLAB_STAGES="3", NM_SLAB_XS="3"),
     dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="8"),
-    dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="8", NM_SLAB_PRODUCERS="4"),
+    dict(NM_SLAB_THREADS="256", NM_SLAB_SPLIT="16"),
     dict(NM_SLAB_THREADS="256", NM_SLAB_SPLIT="12"),
-    dict(NM_SLAB_THREADS="128", NM_SLAB_SPLIT="32"),
+    dict(NM_SLAB_THREADS="256", NM_SLAB_SPLIT="20", NM_SLAB_ENTRIES="4096", NM_SLAB_DISTINCT="720"),
+    dict(NM_SLAB_THREADS="128", NM_SLAB_SPLIT="16", NM_SLAB_ENTRIES="1792", NM_SLAB_DISTINCT="380"),
     dict(NM_SLAB_THREADS="128", NM_SLAB_SPLIT="16", NM_SLAB_ENTRIES="1792", NM_SLAB_DISTINCT="380", NM_SLAB_STAGES="3", NM_SLAB_XS="3"),
-    dict(NM_SLAB_THREADS="256", NM_SLAB_SPLIT="8", NM_SLAB_ENTRIES="2048", NM_SLAB_DISTINCT="420", NM_SLAB_STAGES="3", NM_SLAB_XS="2"),
-    dict(NM_SLAB_THREADS="256", NM_SLAB_ENTRIES="5120", NM_SLAB_DISTINCT="900", NM_SLAB_STAGES="3", NM_SLAB_XS="2"),
 ]
 
 
