@@ -36,12 +36,12 @@ struct NmSlabHost {
 static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std::vector<int>& idx, int n, int R,
                             int ncolb, int sm_count) {
   H.nchunk = 0;
-  // defaults from the B200 sweep (tools/sweep_slab.py, profiles/): R = 3 (B~): 256 threads, <= 16 entries per lane;
-  // R = 1 (Ap~): 512 threads, <= 8 entries per lane
-  int T = nm_env_int("NM_SLAB_THREADS", R == 3 ? 256 : 512);
+  // defaults from the B200 sweep (tools/sweep_slab.py, profiles/r1d_sweep_slab.json): 256 lanes per chunk (8 consumer
+  // warps), <= 12 entries per lane, 2 stages + 2 x buffers (2 CTAs per SM), 4 producer warps
+  int T = nm_env_int("NM_SLAB_THREADS", 256);
   if (T != 64 && T != 128 && T != 256 && T != 512) T = 256;
   const int NW = T / 32;
-  const int lcap = std::max(2, nm_env_int("NM_SLAB_SPLIT", R == 3 ? 16 : 8));  // entries one lane walks at most
+  const int lcap = std::max(2, nm_env_int("NM_SLAB_SPLIT", 12));               // entries one lane walks at most
   const int ecap = std::max(32, nm_env_int("NM_SLAB_ENTRIES", 3584));          // (estimated) padded entries per chunk
   const int dcap = std::max(16, std::min(16384, nm_env_int("NM_SLAB_DISTINCT", R == 3 ? 640 : 1536)));
   auto len_of = [&](int row) { return rp[row + 1] - rp[row]; };
