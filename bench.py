@@ -323,14 +323,14 @@ def main():
     infoB = mvmod.parcsr_info(mv.sBV)
     kind = C.c_int(); pbytes = C.c_longlong()
     _lib.check(L.nm_chebiter_pack_info(mv.chebB, C.byref(kind), C.byref(pbytes)))
-    kname = ("k_spmv_kron3<EpiCheb>", "k_pack<KRON3,EpiCheb>", "k_sell<KRON3,EpiCheb>", "k_slab<3,EpiCheb>")[kind.value]
+    kname = ("k_spmv_kron3<EpiCheb>", "k_pack<KRON3,EpiCheb>", "k_sell<KRON3,EpiCheb>", "k_slab<3,256,EpiCheb>", "k_slabws<3,8,EpiCheb>")[kind.value]
     bytes_launch = cheb_step_bytes(infoB["nnz"], infoB["nrow"])
     fmt_bytes_launch = pbytes.value + 48 * infoB["nrow"]
     achieved = bytes_launch / (us_launch * 1e-6) / 1e9
     traffic = None                      # dram bytes per launch of this kernel from the committed ncu --set full capture
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if kind.value == 3 and nr == 1 and tj.get("n_rows") == infoB["nrow"]:
+        if kind.value == tj.get("kind") and nr == 1 and tj.get("n_rows") == infoB["nrow"]:
             traffic = tj["traffic_bytes_per_launch"]
     except Exception:
         pass

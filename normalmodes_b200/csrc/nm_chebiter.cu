@@ -160,13 +160,13 @@ extern "C" int nm_chebiter_solve_dev(void* h, const double* b_dev, double* x_dev
   NM_API_END
 }
 // kind: 0 = plain kernels on the caller's numbering, 1 = TMA-staged packed kernel (k_pack), 2 = sliced JDS (k_sell),
-// 3 = TMA-staged warp-sliced ELL slabs (k_slab), all three on vectors kept in pack order; bytes = matrix bytes one iteration step streams
+// 3 = TMA-staged warp-sliced ELL slabs (k_slab), 4 = the same, warp-specialised (k_slabws); all on vectors kept in pack order; bytes = matrix bytes one iteration step streams
 extern "C" int nm_chebiter_pack_info(void* h, int* kind, long long* bytes) {
   NM_API_BEGIN
   NmChebIter& C = *(NmChebIter*)h;
-  const int k = C.pslab.nchunk > 0 ? 3 : (C.psell.nchunk > 0 ? 2 : (C.ppack.nchunk > 0 ? 1 : 0));
+  const int k = C.pslab.nchunk > 0 ? (C.pslab.ws ? 4 : 3) : (C.psell.nchunk > 0 ? 2 : (C.ppack.nchunk > 0 ? 1 : 0));
   if (kind) *kind = k;
-  if (bytes) *bytes = k == 3 ? C.pslab.bytes : (k == 2 ? C.psell.bytes : (k == 1 ? C.ppack.bytes : C.M->fmt_bytes));
+  if (bytes) *bytes = k >= 3 ? C.pslab.bytes : (k == 2 ? C.psell.bytes : (k == 1 ? C.ppack.bytes : C.M->fmt_bytes));
   NM_API_END
 }
 // diagnostic (NM_SLAB_TRACE=1): clock64 stamps of the last k_slab launch, [grid][64 chunks][8 stamps]; returns grid
