@@ -182,7 +182,7 @@ struct NmSell {
 // A chunk is one contiguous 16-byte aligned blob (header, slice table, values, distinct column ids, 16-bit
 // chunk-local column indices) moved by one TMA bulk copy.  Vectors live in pack order (row j of chunk c is
 // element first(c)+j).
-struct NmSlabHeader { int nr, nd, nslice, first, nep, gmax, pad1, pad2; };   // 32 bytes; gmax: most lanes per row
+struct NmSlabHeader { int nr, nd, nslice, first, nep, gmax, has_ghost, pad2; };   // 32 bytes; gmax: most lanes per row
 struct NmSlab {
   DBuf<unsigned char> blob;
   DBuf<NmPackDesc> desc;
@@ -292,6 +292,11 @@ NmParcsr* nm_parcsr_build(int nrow_glob, int ncol_glob, const int* row_starts, c
                           const int* ia, const int* ja, const double* a);
 NmParcsr* nm_parcsr_scaled_copy(const NmParcsr& M, const double* drow_dev, const double* dcol_dev);
 void nm_halo_exchange(NmParcsr& M, const double* x, const int* send_idx = nullptr);   // send_idx: override of the pack list
+// Peer-window exchange WITHOUT the arrival wait: pushes x to the peers and raises the flags; the consumer kernel polls
+// (out: this rank's flag array, the sources to wait for, the flag value).  Returns false when the matrix uses NCCL or
+// has no halo (then nothing was done and the caller uses nm_halo_exchange).
+struct NmHaloWait { const unsigned long long* flags; unsigned mask; unsigned long long epoch; int* status; };
+bool nm_halo_push_nowait(NmParcsr& M, const double* x, const int* send_idx, NmHaloWait* w);
 void nm_spmv(NmParcsr& M, const double* x, double* y);                 // y = M x   (device pointers)
 void nm_spmv_add(NmParcsr& M, const double* x, double* y);             // y += M x
 // packed format (nm_pack.cu): rp/idx = host row pointers and column ids of the chosen format, n (block-)rows

@@ -26,9 +26,14 @@ struct NmPushArgs {
   unsigned long long epoch;
   unsigned* ctr;
   int* status;
+  int wait;                                 // 1: the last block waits for the peers' flags; 0: the consumer kernel polls
 };
 
 __global__ void k_halo_push(NmPushArgs A, const double* __restrict__ x, const int* __restrict__ idx) {
+  // programmatic dependent launch (no-ops for plain launches): let the consumer kernel start its matrix prefetch,
+  // and make sure the producer of x has completed before x is read
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.nsend; i += gridDim.x * blockDim.x) {
     int r = 0;
     while (i >= A.send_off[r + 1]) ++r;
@@ -48,7 +53,7 @@ __global__ void k_halo_push(NmPushArgs A, const double* __restrict__ x, const in
     if (A.send_mask & (1u << r)) {
       asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.peer_flag[r]), "l"(A.epoch) : "memory");
     }
-    if (A.recv_mask & (1u << r)) {
+    if (A.wait && (A.recv_mask & (1u << r))) {
       const unsigned long long* f = A.my_flag + r;
       unsigned long long v;
       const long long t0 = clock64();
@@ -62,33 +67,57 @@ __global__ void k_halo_push(NmPushArgs A, const double* __restrict__ x, const in
   if (threadIdx.x == 0) *A.ctr = 0;
 }
 
+static void halo_push_launch(NmParcsr& M, const double* x, const int* send_idx, int wait, NmHaloWait* w) {
+  NmCtx& c = nm_ctx();
+  NmHalo& h = M.halo;
+  const unsigned long long epoch = ++h.epoch;
+  const int par = (int)(epoch & 1);
+  NmPushArgs A;
+  A.nranks = c.nranks; A.me = c.rank; A.nsend = h.nsend;
+  A.recv_mask = A.send_mask = 0;
+  for (int r = 0; r < 8; ++r) { A.peer_xg[r] = nullptr; A.peer_flag[r] = nullptr; }
+  for (int r = 0; r <= 8; ++r) A.send_off[r] = r <= c.nranks ? h.send_off[std::min(r, c.nranks)] : h.nsend;
+  for (int r = 0; r < c.nranks; ++r) {
+    if (r == c.rank) continue;
+    if (h.send_cnt[r] > 0) {
+      A.send_mask |= 1u << r;
+      A.peer_xg[r] = (double*)(c.peer_win[r] + h.peer_xg[par][r]) + h.peer_base[r];
+      A.peer_flag[r] = (unsigned long long*)(c.peer_win[r] + h.peer_flag[r]) + c.rank;
+    }
+    if (h.recv_cnt[r] > 0) A.recv_mask |= 1u << r;
+  }
+  A.my_flag = (const unsigned long long*)(c.win + h.win_flag);
+  A.epoch = epoch; A.ctr = c.push_ctr; A.status = c.dev_status; A.wait = wait;
+  const int blocks = std::max(1, std::min(16, nm_div_up(h.nsend, 2048)));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = 0; cfg.stream = c.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = wait ? 0 : 1;               // chained into the ChebIter steps' dependent launches
+  NM_CUDA(cudaLaunchKernelEx(&cfg, k_halo_push, A, x, send_idx ? send_idx : (const int*)h.send_idx.p));
+  c.launches++;
+  h.xg_cur = (double*)(c.win + h.win_xg[par]);
+  if (w) { w->flags = A.my_flag; w->mask = A.recv_mask; w->epoch = epoch; w->status = c.dev_status; }
+}
+
+bool nm_halo_push_nowait(NmParcsr& M, const double* x, const int* send_idx, NmHaloWait* w) {
+  NmCtx& c = nm_ctx();
+  NmHalo& h = M.halo;
+  w->flags = nullptr; w->mask = 0; w->epoch = 0; w->status = nullptr;
+  if (c.nranks == 1 || (h.nghost == 0 && h.nsend == 0)) return true;       // nothing to exchange, nothing to wait for
+  if (!h.p2p) return false;
+  halo_push_launch(M, x, send_idx, 0, w);
+  return true;
+}
+
 void nm_halo_exchange(NmParcsr& M, const double* x, const int* send_idx) {
   NmCtx& c = nm_ctx();
   NmHalo& h = M.halo;
   if (c.nranks == 1 || (h.nghost == 0 && h.nsend == 0)) return;
   if (h.p2p) {
-    const unsigned long long epoch = ++h.epoch;
-    const int par = (int)(epoch & 1);
-    NmPushArgs A;
-    A.nranks = c.nranks; A.me = c.rank; A.nsend = h.nsend;
-    A.recv_mask = A.send_mask = 0;
-    for (int r = 0; r < 8; ++r) { A.peer_xg[r] = nullptr; A.peer_flag[r] = nullptr; }
-    for (int r = 0; r <= 8; ++r) A.send_off[r] = r <= c.nranks ? h.send_off[std::min(r, c.nranks)] : h.nsend;
-    for (int r = 0; r < c.nranks; ++r) {
-      if (r == c.rank) continue;
-      if (h.send_cnt[r] > 0) {
-        A.send_mask |= 1u << r;
-        A.peer_xg[r] = (double*)(c.peer_win[r] + h.peer_xg[par][r]) + h.peer_base[r];
-        A.peer_flag[r] = (unsigned long long*)(c.peer_win[r] + h.peer_flag[r]) + c.rank;
-      }
-      if (h.recv_cnt[r] > 0) A.recv_mask |= 1u << r;
-    }
-    A.my_flag = (const unsigned long long*)(c.win + h.win_flag);
-    A.epoch = epoch; A.ctr = c.push_ctr; A.status = c.dev_status;
-    const int blocks = std::max(1, std::min(16, nm_div_up(h.nsend, 2048)));
-    k_halo_push<<<blocks, 512, 0, c.stream>>>(A, x, send_idx ? send_idx : h.send_idx.p);
-    c.launches++;
-    h.xg_cur = (double*)(c.win + h.win_xg[par]);
+    halo_push_launch(M, x, send_idx, 1, nullptr);
     return;
   }
   if (h.nsend > 0) {

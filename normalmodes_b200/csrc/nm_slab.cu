@@ -185,6 +185,7 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
   slot_off8.reserve((size_t)rp[n]);
   slot_src.reserve((size_t)rp[n]);
   std::vector<int> cols, lidx_of(ncolb, -1);
+  std::vector<char> ghost_chunk(nchunk, 0);
   std::vector<std::vector<int>> rem;
   const bool bank_aware = nm_env_int("NM_PACK_BANK_AWARE", 1) != 0;
   for (int i = 0; i < nchunk; ++i) {
@@ -195,7 +196,12 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
     const short* lane_row = lane_row_all.data() + c.lane_off;
     int gmax = 1;
     for (int j = 0; j < c.nr; ++j) gmax = std::max(gmax, lanes_of(len_of(rows[j])));
-    NmSlabHeader h{c.nr, c.nd, nslice, c.first, nep, gmax, 0, 0};
+    int has_ghost = 0;                                            // any column owned by another rank (id >= n)
+    for (int j = 0; j < c.nr && !has_ghost; ++j)
+      for (int p = rp[rows[j]]; p < rp[rows[j] + 1]; ++p)
+        if (idx[p] >= n) { has_ghost = 1; break; }
+    ghost_chunk[i] = (char)has_ghost;
+    NmSlabHeader h{c.nr, c.nd, nslice, c.first, nep, gmax, has_ghost, 0};
     memcpy(base, &h, sizeof(h));
     const size_t o_tbl = 32;
     const size_t o_val = 32 + up16(8 * (size_t)nslice);
@@ -326,6 +332,15 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
     }
     H.cta_first[grid] = ci;
     NM_REQUIRE(ci == nchunk, "slab: chunk split lost chunks (%d of %d)", ci, nchunk);
+  }
+  // processing order inside a CTA's range: chunks without ghost columns first, so that on several GPUs the chunks
+  // that need the peers' values come last and the halo exchange overlaps the interior ones (the row positions are in
+  // the blob headers: the order of the descriptors is free)
+  for (int g = 0; g < grid; ++g) {
+    std::vector<NmPackDesc> in, bd;
+    for (int ci = H.cta_first[g]; ci < H.cta_first[g + 1]; ++ci) (ghost_chunk[ci] ? bd : in).push_back(desc[ci]);
+    std::copy(in.begin(), in.end(), desc.begin() + H.cta_first[g]);
+    std::copy(bd.begin(), bd.end(), desc.begin() + H.cta_first[g] + in.size());
   }
   H.grid = grid;
   H.padded_entries = pentries;

@@ -208,7 +208,32 @@ struct NmSlabWsArgs {
   NmSlabArgs a;
   int nxs;                  // x buffers in the ring
   int np;                   // producer warps
+  // several GPUs: arrival flags of the ghost values this step gathers (raised by the peers' k_halo_push); polled by
+  // the producers before the first chunk that has ghost columns (those come last in every CTA's range)
+  const unsigned long long* hflags;
+  unsigned hmask;
+  unsigned long long hepoch;
+  int* hstatus;
 };
+
+// ghost values were written by a peer GPU during this kernel's lifetime: read them through L2 (no L1 allocation)
+__device__ __forceinline__ double nm_ld_cg(const double* p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+template <int R>
+__device__ __forceinline__ void nm_slab_gather_ghost(const NmSlabView& v, double* xs, const double* __restrict__ x,
+                                                     const double* xg, int ncol, int t, int nthreads) {
+  const int tot = R * v.h.nd;
+  for (int j = t; j < tot; j += nthreads) {
+    const int node = (R == 1) ? j : j / 3;
+    const int c = R * v.scols[node] + (j - R * node);
+    if (c < ncol) nm_cp_async8(xs + j, x + c);
+    else xs[j] = nm_ld_cg(xg + (c - ncol));
+  }
+  __threadfence_block();                                         // the plain stores above precede the barrier arrival
+}
 
 template <int R, int NC, class Epi>
 __global__ void __launch_bounds__(32 * (NC + 8)) k_slabws(NmSlabWsArgs W, Epi epi) {
@@ -257,6 +282,7 @@ __global__ void __launch_bounds__(32 * (NC + 8)) k_slabws(NmSlabWsArgs W, Epi ep
     const double* __restrict__ xg = A.xg;
     const int ncol = A.ncol;
     asm volatile("griddepcontrol.wait;" ::: "memory");           // the previous step's vectors are complete and visible
+    bool flags_seen = false;
     for (int it = 0; it < nmine; ++it) {
       // a. x values of chunk it -> xs[it % X] (free once the consumers are done with chunk it - X)
       const int s = it % S, xb = it % X;
@@ -264,7 +290,27 @@ __global__ void __launch_bounds__(32 * (NC + 8)) k_slabws(NmSlabWsArgs W, Epi ep
       if (it >= X) nm_mbar_wait_bounded(empty_xs + xb, (uint32_t)(((it / X) - 1) & 1));
       const NmSlabView v = nm_slab_view(stage0 + (size_t)s * A.stage_bytes);
       double* xs = xs0 + (size_t)xb * A.xs_doubles;
-      nm_slab_gather<R>(v, xs, x, xg, ncol, ptid, pthreads);
+      if (v.h.has_ghost && W.hmask) {
+        if (!flags_seen) {
+          if (lane == 0) {
+            for (int r = 0; r < 8; ++r) {
+              if (!(W.hmask & (1u << r))) continue;
+              unsigned long long f;
+              const long long t0 = clock64();
+              for (;;) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(W.hflags + r) : "memory");
+                if (f >= W.hepoch) break;
+                if (clock64() - t0 > 20000000000ll) { atomicOr(W.hstatus, 1); break; }   // ~10 s: peer stalled or died
+              }
+            }
+          }
+          __syncwarp();
+          flags_seen = true;
+        }
+        nm_slab_gather_ghost<R>(v, xs, x, xg, ncol, ptid, pthreads);
+      } else {
+        nm_slab_gather<R>(v, xs, x, xg, ncol, ptid, pthreads);
+      }
       nm_cp_async_mbar_arrive_noinc(full_xs + xb);
       // b. refill the stage of chunk it-1 (consumed once all NC warps released it) with chunk it-1+S
       if (ptid == 0 && it >= 1) {
@@ -330,7 +376,7 @@ __global__ void __launch_bounds__(32 * (NC + 8)) k_slabws(NmSlabWsArgs W, Epi ep
 }
 
 template <int R, int NC, class Epi>
-static inline void nm_slabws_launch_t(NmParcsr& M, NmSlab& S, const double* x, const Epi& epi) {
+static inline void nm_slabws_launch_t(NmParcsr& M, NmSlab& S, const double* x, const Epi& epi, const NmHaloWait& hw) {
   NmCtx& c = nm_ctx();
   NmSlabWsArgs W;
   NmSlabArgs& A = W.a;
@@ -339,6 +385,7 @@ static inline void nm_slabws_launch_t(NmParcsr& M, NmSlab& S, const double* x, c
   A.stage_bytes = S.stage_bytes; A.xs_doubles = S.xs_doubles; A.nstage = S.nstage;
   A.trace = nullptr;
   W.nxs = S.nxs; W.np = S.nprod;
+  W.hflags = hw.flags; W.hmask = hw.mask; W.hepoch = hw.epoch; W.hstatus = hw.status;
   static bool attr_set = false;                                  // per template instantiation
   if (!attr_set) {
     NM_CUDA(cudaFuncSetAttribute(k_slabws<R, NC, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -375,20 +422,28 @@ static inline void nm_slab_launch_t(NmParcsr& M, NmSlab& S, const double* x, con
 // Product through the slabs: x and the epilogue vectors are in pack order (S.order).
 template <class Epi>
 static inline void nm_spmv_slab_epi(NmParcsr& M, NmSlab& S, const double* x, const Epi& epi, const int* send_idx) {
-  nm_halo_exchange(M, x, send_idx);
   const bool blk = M.format == NM_FMT_KRON3;
   if (S.ws) {
+    // several GPUs: push without waiting -- the kernel's producers poll the arrival flags before the chunks that have
+    // ghost columns, so the exchange overlaps the launch, the matrix prefetch and the interior chunks
+    NmHaloWait hw;
+    static const bool overlap = nm_env_int("NM_HALO_OVERLAP", 1) != 0;
+    if (!overlap || !nm_halo_push_nowait(M, x, send_idx, &hw)) {
+      nm_halo_exchange(M, x, send_idx);
+      hw.flags = nullptr; hw.mask = 0; hw.epoch = 0; hw.status = nullptr;
+    }
     if (S.threads == 512) {
-      if (blk) nm_slabws_launch_t<3, 16, Epi>(M, S, x, epi); else nm_slabws_launch_t<1, 16, Epi>(M, S, x, epi);
+      if (blk) nm_slabws_launch_t<3, 16, Epi>(M, S, x, epi, hw); else nm_slabws_launch_t<1, 16, Epi>(M, S, x, epi, hw);
     } else if (S.threads == 256) {
-      if (blk) nm_slabws_launch_t<3, 8, Epi>(M, S, x, epi); else nm_slabws_launch_t<1, 8, Epi>(M, S, x, epi);
+      if (blk) nm_slabws_launch_t<3, 8, Epi>(M, S, x, epi, hw); else nm_slabws_launch_t<1, 8, Epi>(M, S, x, epi, hw);
     } else if (S.threads == 64) {
-      if (blk) nm_slabws_launch_t<3, 2, Epi>(M, S, x, epi); else nm_slabws_launch_t<1, 2, Epi>(M, S, x, epi);
+      if (blk) nm_slabws_launch_t<3, 2, Epi>(M, S, x, epi, hw); else nm_slabws_launch_t<1, 2, Epi>(M, S, x, epi, hw);
     } else {
-      if (blk) nm_slabws_launch_t<3, 4, Epi>(M, S, x, epi); else nm_slabws_launch_t<1, 4, Epi>(M, S, x, epi);
+      if (blk) nm_slabws_launch_t<3, 4, Epi>(M, S, x, epi, hw); else nm_slabws_launch_t<1, 4, Epi>(M, S, x, epi, hw);
     }
     return;
   }
+  nm_halo_exchange(M, x, send_idx);
   if (S.threads == 512) {
     if (blk) nm_slab_launch_t<3, 512, Epi>(M, S, x, epi); else nm_slab_launch_t<1, 512, Epi>(M, S, x, epi);
   } else if (S.threads == 256) {

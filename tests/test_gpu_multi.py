@@ -27,8 +27,17 @@ def _ngpu():
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
 def test_two_ranks_halo_exchange_and_solve():
+    """Default transport: NVLink peer window, push without wait + arrival flags polled inside the ChebIter step kernel."""
     out = _run(2, 29611)
     print(out[-1500:])
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("env", [dict(NM_HALO_OVERLAP="0"), dict(NM_P2P="0")])
+def test_two_ranks_blocking_exchange_and_nccl_fallback(env):
+    """The blocking peer-window exchange (flags awaited in k_halo_push) and the NCCL send/recv fallback."""
+    out = _run(2, 29615, env_extra=dict(env, NM_MP_CASES="prem3k_p1_j2"))
+    print(out[-800:])
 
 
 @pytest.mark.skipif(_ngpu() < 4, reason="needs >= 4 GPUs")
