@@ -43,6 +43,7 @@ __device__ __forceinline__ NmSlabView nm_slab_view(const unsigned char* st) {
   const int4 a = *(const int4*)st;
   const int4 b = *(const int4*)(st + 16);
   v.h.nr = a.x; v.h.nd = a.y; v.h.nslice = a.z; v.h.first = a.w; v.h.nep = b.x; v.h.gmax = b.y;
+  v.h.has_ghost = b.z; v.h.pad2 = 0;
   v.tbl = (const uint2*)(st + 32);
   v.sv = (const double*)(st + 32 + ((8 * v.h.nslice + 15) & ~15));
   v.scols = (const int*)(v.sv + v.h.nep);
