@@ -215,6 +215,7 @@ struct NmSlabWsArgs {
   unsigned hmask;
   unsigned long long hepoch;
   int* hstatus;
+  int ghost_cg;             // 1: read ghost values with ld.global.cg (synchronous); 0: cp.async like the owned ones
 };
 
 // ghost values were written by a peer GPU during this kernel's lifetime: read them through L2 (no L1 allocation)
@@ -308,7 +309,10 @@ __global__ void __launch_bounds__(32 * (NC + 8)) k_slabws(NmSlabWsArgs W, Epi ep
           __syncwarp();
           flags_seen = true;
         }
-        nm_slab_gather_ghost<R>(v, xs, x, xg, ncol, ptid, pthreads);
+        // the ghost buffer of this parity is only read after the flags, and L1 does not outlive a grid (the d buffers
+        // alternate the same way): the asynchronous gather is as safe for ghosts as for owned values
+        if (W.ghost_cg) nm_slab_gather_ghost<R>(v, xs, x, xg, ncol, ptid, pthreads);
+        else nm_slab_gather<R>(v, xs, x, xg, ncol, ptid, pthreads);
       } else {
         nm_slab_gather<R>(v, xs, x, xg, ncol, ptid, pthreads);
       }
@@ -387,6 +391,8 @@ static inline void nm_slabws_launch_t(NmParcsr& M, NmSlab& S, const double* x, c
   A.trace = nullptr;
   W.nxs = S.nxs; W.np = S.nprod;
   W.hflags = hw.flags; W.hmask = hw.mask; W.hepoch = hw.epoch; W.hstatus = hw.status;
+  static const int ghost_cg = nm_env_int("NM_HALO_GHOST_CG", 0);
+  W.ghost_cg = ghost_cg;
   static bool attr_set = false;                                  // per template instantiation
   if (!attr_set) {
     NM_CUDA(cudaFuncSetAttribute(k_slabws<R, NC, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
