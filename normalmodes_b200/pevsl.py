@@ -108,3 +108,16 @@ def pnm_apply_pevsl(mv, lowfreq, upfreq, log=None, maxit=None, tol=1.0e-5, seed=
 def finalize_eigerr(r, N):
     """Turn the (already globally summed) squared residuals into the reference's 'relative err.'."""
     return np.sqrt(r.eigerr / N) / np.abs(r.eigval)
+
+
+def pnm_save_eigenvectors(mv, r, fvdata):
+    """src/mod_pevsl.f90:188-201: eigenvector i (ascending eigenvalue) of this rank's rows, in physical coordinates
+    `EIGVEC * B%diag`, at byte offset `B%sizdist(rank)*8` of `<fvdata>_<i>.dat` (normalmodes_b200.io)."""
+    from . import io
+    return io.save_eigenvectors(fvdata, r.eigvec, mv.B.diag, mv.B.sizdist, mv.rank)
+
+
+def pnm_save_results(names, vlist_local, vtxdist, rank, vstat_local=None):
+    """src/mod_pevsl.f90:225-243: `unstrM%new%vlist` (and `vstat` when the model has fluid) of this rank."""
+    from . import io
+    io.save_vlist_vstat(names, vlist_local, vtxdist, rank, vstat_local)
