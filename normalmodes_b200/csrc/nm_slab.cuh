@@ -1,18 +1,23 @@
-// k_slab: the fused Chebyshev-iteration step (SpMV + three-term vector update, EpiCheb) on the warp-sliced ELL
-// slabs of nm_slab.cu.  Replaces pEVSL parcsrmatvec + the ChebIter AXPYs called through pevsl_chebiter_f90
+// k_slabws / k_slab: the fused Chebyshev-iteration step (SpMV + three-term vector update, EpiCheb) on the warp-sliced
+// ELL slabs of nm_slab.cu.  Replaces pEVSL parcsrmatvec + the ChebIter AXPYs called through pevsl_chebiter_f90
 // (src/mod_matvec.f90:480,512; B-solve registration src/mod_pevsl.f90:72-73).
 //
 // HBM-bound streaming work (0.2 flop/B): no tensor cores.  Why this shape (ncu of the predecessor k_pack,
 // profiles/r1b_kpack_summary.md): with L lanes per row, a JDS offset table and a shared-memory partial-sum
 // reduction the walk cost ~480 warp instructions per chunk and warp, only 3% of them DFMA, and the kernel sat
-// at 52% issue utilisation / 28% of HBM.  Here a chunk holds at most T lanes and ONE THREAD walks ONE index row
+// at 52% issue utilisation / 28% of HBM.  Here a chunk holds at most T lanes and ONE LANE walks ONE index row
 // (R = 3 scalar rows of a node for B = M (x) I3, R = 1 for Ap~; rows longer than NM_SLAB_SPLIT entries are
-// shared by an aligned group of 2, 4, ... lanes and combined with shuffles): the inner loop is
+// shared by adjacent lanes of one warp and combined with a segmented shuffle tree): the inner loop is
 //     LDS.64 value, LDS.U16 local column, R x LDS.64 x, R x DFMA
-// with stride-32 conflict-free value/index reads, the row sums stay in registers, and the fused epilogue follows
-// the walk directly -- one __syncthreads per chunk.  The matrix is streamed by TMA bulk copies (cp.async.bulk +
-// mbarrier complete_tx, L2 evict-first so the vectors stay L2-resident) through an NSTAGE ring; the x values of
-// the NEXT chunk are gathered once per distinct column with cp.async while the current chunk is walked.
+// with stride-32 conflict-free value/index reads, the row sums stay in registers and the fused epilogue follows the
+// walk directly.  The matrix is streamed by TMA bulk copies (cp.async.bulk + mbarrier complete_tx, L2 evict-first so
+// the vectors stay L2-resident) through a stage ring; the x values of the chunks AHEAD are gathered once per distinct
+// column with cp.async.
+//   k_slab    one __syncthreads per chunk (all warps gather, then walk);
+//   k_slabws  (default) warp-specialised: producer warps keep the rings full, consumer warps only walk; stages and x
+//             buffers are handed over with full/empty mbarriers; consecutive steps are chained by programmatic
+//             dependent launch; on several GPUs the producers poll the peers' arrival flags before the chunks that
+//             have ghost columns (nm_parcsr.cu: k_halo_push).
 #pragma once
 #include "nm_spmv.cuh"
 

@@ -11,7 +11,11 @@
 //   KRON3  B = M (x) I3 (src/mod_cg_create_matrix.f90:1247-1259,1417-1434): scalar values and one
 //          block-column id per 3x3 block -> 12 bytes per 3 non-zeros of each of the 3 rows.
 //
-// Main kernel (k_pack): HBM-bound streaming work, no tensor cores.  The matrix is stored once more in the
+// The Chebyshev iterations (the hot loop) run on k_slabws / k_slab of nm_slab.cuh; the kernels in this file are the
+// general products (A, Ad, E, ET with the fused filter epilogue), the round-1a iteration kernels kept as fallbacks
+// and regression references (k_pack, k_sell), and the plain subwarp-per-row kernels.
+//
+// k_pack: HBM-bound streaming work, no tensor cores.  The matrix is stored once more in the
 // packed row-block format of nm_pack.cu: locality-ordered rows cut into chunks, each chunk one contiguous blob
 // (values in jagged-diagonal order, the chunk's row ids, its DISTINCT column ids, 16-bit chunk-local column
 // indices).  A persistent CTA walks a contiguous range of chunks; one elected thread moves each blob into
