@@ -60,6 +60,7 @@ __global__ void k_halo_push(NmPushArgs A, const double* __restrict__ x, const in
       for (;;) {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
         if (v >= A.epoch) break;
+        if (*(volatile int*)A.status != 0) break;                                 // an earlier wait already failed
         if (clock64() - t0 > 20000000000ll) { atomicOr(A.status, 1); break; }     // ~10 s: peer stalled or died
       }
     }

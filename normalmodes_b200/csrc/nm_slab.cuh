@@ -307,7 +307,10 @@ __global__ void __launch_bounds__(32 * (NC + 8)) k_slabws(NmSlabWsArgs W, Epi ep
               for (;;) {
                 asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(W.hflags + r) : "memory");
                 if (f >= W.hepoch) break;
-                if (clock64() - t0 > 20000000000ll) { atomicOr(W.hstatus, 1); break; }   // ~10 s: peer stalled or died
+                // ~10 s: peer stalled or died; once the status word is set every later wait gives up at once, so a
+                // failed run ends at the host's next status check instead of stalling per kernel
+                if (*(volatile int*)W.hstatus != 0) break;
+                if (clock64() - t0 > 20000000000ll) { atomicOr(W.hstatus, 1); break; }
               }
             }
           }
