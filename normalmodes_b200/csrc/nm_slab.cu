@@ -187,11 +187,14 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
   std::vector<int> cols, lidx_of(ncolb, -1);
   std::vector<char> ghost_chunk(nchunk, 0);
   std::vector<std::vector<int>> rem;
-  const bool bank_aware = nm_env_int("NM_PACK_BANK_AWARE", 1) != 0;
+  const int bank_mode = std::max(0, std::min(3, nm_env_int("NM_PACK_BANK_AWARE", 3)));
   for (int i = 0; i < nchunk; ++i) {
     const Chunk& c = chunks[i];
     unsigned char* base = blob.data() + start[i];
     const int nslice = c.nslice, nep = nep_of[i];
+    const size_t nslot_before = slot_src.size();
+    size_t chunk_entries = 0;
+    for (int j = 0; j < c.nr; ++j) chunk_entries += (size_t)len_of(final_order[c.first + j]);
     const int* rows = final_order.data() + c.first;
     const short* lane_row = lane_row_all.data() + c.lane_off;
     int gmax = 1;
@@ -233,12 +236,17 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
     NM_REQUIRE((int)cols.size() == c.nd, "slab: distinct-column count mismatch");
     for (int j = 0; j < c.nd; ++j) { lidx_of[cols[j]] = j; bcols[j] = colid(cols[j]); }
     const size_t val8 = (start[i] + o_val) / 8;                   // blob position of the value region in doubles
-    // entries still to be placed, per local row (shared by the lanes of the row)
-    if ((int)rem.size() < c.nr) rem.resize(c.nr);
-    for (int j = 0; j < c.nr; ++j) {
-      rem[j].clear();
-      for (int p = rp[rows[j] + 1] - 1; p >= rp[rows[j]]; --p) rem[j].push_back(p);    // back() = first in CSR order
-    }
+    // The ORDER in which the lanes of a row walk its entries is free (it only reassociates the row sum,
+    // deterministically); it decides how many shared-memory wavefronts the x reads of a half-warp step cost: 16 lanes
+    // x 8 bytes are one wavefront when they hit 16 different bank pairs (bank pair = local column mod 16) OR the same
+    // address.  NM_PACK_BANK_AWARE:
+    //   3 (default) share-aware greedy: per step the most constrained lane chooses first; it prefers an entry whose
+    //     column another lane of the half-warp already reads at this step (same address: free), then an empty bank
+    //     pair, then the least loaded one; the lanes of a split row draw from one pool.  Modelled x wavefronts on the
+    //     bench workload (nm_slab_host_selftest): 1.27 x the conflict-free count;
+    //   2 edge colouring of the bipartite multigraph lanes x bank pairs with the steps as colours (ignores sharing): 1.81 x;
+    //   1 lane-by-lane first free bank pair (round 1c; ncu: 31% of the shared wavefronts were replays): 1.9-2.0 x;
+    //   0 CSR order: 2.4 x.
     int eoff = 0;
     for (int s = 0; s < nslice; ++s) {
       const int t0 = 32 * s;
@@ -246,22 +254,136 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
       for (int l = 0; l < 32; ++l) if (lane_row[t0 + l] >= 0) w = std::max(w, vlen_of(rows[lane_row[t0 + l]]));
       tbl[2 * s] = (unsigned)eoff;
       tbl[2 * s + 1] = (unsigned)w;
-      for (int k = 0; k < w; ++k)
-        for (int h0 = 0; h0 < 32; h0 += 16) {
-          unsigned taken = 0, was_real = 0;
-          // real entries first, then the padding lanes take bank pairs that are still free
+      // lane -> its entries (CSR positions): round-robin over the row's lanes, or (share-aware greedy) one pool per
+      // row kept by its first lane and drawn from by all of them
+      std::vector<int> lane_ent[32];
+      int pool_of[32];
+      for (int l = 0; l < 32;) {
+        const int j = lane_row[t0 + l];
+        pool_of[l] = l;
+        if (j < 0) { ++l; continue; }
+        int g = 1;
+        while (l + g < 32 && lane_row[t0 + l + g] == j) ++g;
+        int e = 0;
+        for (int p = rp[rows[j]]; p < rp[rows[j] + 1]; ++p, ++e) lane_ent[bank_mode == 3 ? l : l + e % g].push_back(p);
+        for (int q = 0; q < g; ++q) pool_of[l + q] = bank_mode == 3 ? l : l + q;
+        l += g;
+      }
+      // step of every entry: sched[l][k] = CSR position walked by lane l at step k, or -1 (padding)
+      std::vector<int> sched(32 * (size_t)std::max(w, 1), -1);
+      for (int h0 = 0; h0 < 32; h0 += 16) {
+        if (bank_mode == 2) {
+          // edges of the half-warp
+          struct Edge { int lane, bank, src, col; };
+          std::vector<Edge> E;
+          int bankdeg[16] = {0};
+          for (int l = h0; l < h0 + 16; ++l)
+            for (int p : lane_ent[l]) { const int bk = lidx_of[idx[p]] & 15; E.push_back({l - h0, bk, p, -1}); bankdeg[bk]++; }
+          int C = w;
+          for (int q = 0; q < 16; ++q) C = std::max(C, bankdeg[q]);
+          std::vector<int> lane_col(16 * (size_t)C, -1), bank_col(16 * (size_t)C, -1);     // [vertex][colour] -> edge
+          for (int ei = 0; ei < (int)E.size(); ++ei) {
+            const int u = E[ei].lane, v = E[ei].bank;
+            int ca = 0, cb = 0;
+            while (lane_col[(size_t)u * C + ca] >= 0) ++ca;                              // free at the lane
+            while (bank_col[(size_t)v * C + cb] >= 0) ++cb;                              // free at the bank pair
+            if (bank_col[(size_t)v * C + ca] >= 0) {
+              // free colour ca at v: swap ca <-> cb along the alternating path that starts at v with its ca edge
+              std::vector<int> path;
+              int bankv = v, col = ca;
+              for (;;) {
+                const int e1 = bank_col[(size_t)bankv * C + col];                        // bank --col--> lane
+                if (e1 < 0) break;
+                path.push_back(e1);
+                const int other = col == ca ? cb : ca;
+                const int e2 = lane_col[(size_t)E[e1].lane * C + other];                  // lane --other--> bank
+                if (e2 < 0) break;
+                path.push_back(e2);
+                bankv = E[e2].bank;
+              }
+              for (int pe : path) {                                                       // clear, then set swapped
+                lane_col[(size_t)E[pe].lane * C + E[pe].col] = -1;
+                bank_col[(size_t)E[pe].bank * C + E[pe].col] = -1;
+              }
+              for (int pe : path) {
+                E[pe].col = E[pe].col == ca ? cb : ca;
+                lane_col[(size_t)E[pe].lane * C + E[pe].col] = pe;
+                bank_col[(size_t)E[pe].bank * C + E[pe].col] = pe;
+              }
+            }
+            E[ei].col = ca;
+            lane_col[(size_t)u * C + ca] = ei;
+            bank_col[(size_t)v * C + ca] = ei;
+          }
+          // colours < w are steps; the few entries coloured >= w (an overloaded bank pair) take free steps of their lane
+          std::vector<int> over;
+          for (int ei = 0; ei < (int)E.size(); ++ei) {
+            if (E[ei].col < w) sched[(size_t)(h0 + E[ei].lane) * w + E[ei].col] = E[ei].src;
+            else over.push_back(ei);
+          }
+          for (int ei : over) {
+            const int l = h0 + E[ei].lane;
+            int k = 0;
+            while (k < w && sched[(size_t)l * w + k] >= 0) ++k;
+            NM_REQUIRE(k < w, "slab: lane with more entries than its slice is wide");
+            sched[(size_t)l * w + k] = E[ei].src;
+          }
+        } else if (bank_mode == 3) {
+          // share-aware greedy: lanes that read the SAME x value in the same step share a wavefront, so a lane first
+          // looks for an entry whose column another lane of the half-warp already reads at this step, then for an
+          // empty bank pair, then for the least loaded one
+          for (int k = 0; k < w; ++k) {
+            int naddr[16] = {0};
+            int addr[16][16];
+            int lanes[16];
+            for (int q = 0; q < 16; ++q) lanes[q] = h0 + q;
+            // most constrained lanes (fewest candidates left) choose first
+            std::stable_sort(lanes, lanes + 16, [&](int a, int b) { return lane_ent[pool_of[a]].size() < lane_ent[pool_of[b]].size(); });
+            for (int q0 = 0; q0 < 16; ++q0) {
+              const int l = lanes[q0];
+              std::vector<int>& rj = lane_ent[pool_of[l]];
+              if (lane_row[t0 + l] < 0 || rj.empty()) continue;
+              int pick = 0, best = 1 << 30;
+              for (int q = 0; q < (int)rj.size(); ++q) {
+                const int li = lidx_of[idx[rj[q]]], bk = li & 15;
+                int score = 2 + 2 * naddr[bk];
+                for (int z = 0; z < naddr[bk]; ++z) if (addr[bk][z] == li) { score = 0; break; }
+                if (score == 2) score = 1;
+                if (score < best) { best = score; pick = q; if (score == 0) break; }
+              }
+              const int src = rj[pick];
+              rj.erase(rj.begin() + pick);
+              const int li = lidx_of[idx[src]], bk = li & 15;
+              bool dup = false;
+              for (int z = 0; z < naddr[bk]; ++z) dup = dup || addr[bk][z] == li;
+              if (!dup) addr[bk][naddr[bk]++] = li;
+              sched[(size_t)l * w + k] = src;
+            }
+          }
+        } else {
+          for (int k = 0; k < w; ++k) {
+            unsigned taken = 0;
+            for (int l = h0; l < h0 + 16; ++l) {
+              std::vector<int>& rj = lane_ent[l];
+              if (rj.empty()) continue;
+              int pick = 0;
+              if (bank_mode == 1)
+                for (int q = 0; q < (int)rj.size(); ++q)
+                  if (!(taken & (1u << (lidx_of[idx[rj[q]]] & 15)))) { pick = q; break; }
+              const int src = rj[pick];
+              rj.erase(rj.begin() + pick);
+              taken |= 1u << (lidx_of[idx[src]] & 15);
+              sched[(size_t)l * w + k] = src;
+            }
+          }
+        }
+        // write the half-warp's steps; padding lanes (value 0.0) point at a bank pair that is still free
+        for (int k = 0; k < w; ++k) {
+          unsigned taken = 0;
           for (int l = h0; l < h0 + 16; ++l) {
-            if (lane_row[t0 + l] < 0) continue;
-            std::vector<int>& rj = rem[lane_row[t0 + l]];
-            if (rj.empty()) continue;
-            was_real |= 1u << (l - h0);
+            const int src = sched[(size_t)l * w + k];
+            if (src < 0) continue;
             const int p = eoff + 32 * k + l;
-            int pick = (int)rj.size() - 1;
-            if (bank_aware)
-              for (int q = (int)rj.size() - 1; q >= 0; --q)
-                if (!(taken & (1u << (lidx_of[idx[rj[q]]] & 15)))) { pick = q; break; }
-            const int src = rj[pick];
-            rj.erase(rj.begin() + pick);
             const int li = lidx_of[idx[src]];
             taken |= 1u << (li & 15);
             bidx[p] = (unsigned short)li;
@@ -269,8 +391,7 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
             slot_src.push_back(src);
           }
           for (int l = h0; l < h0 + 16; ++l) {
-            if (was_real & (1u << (l - h0))) continue;
-            // padding: value stays 0.0; point it at a free bank pair (any valid local column)
+            if (sched[(size_t)l * w + k] >= 0) continue;
             int li = 0;
             for (int q = 0; q < 16 && q < c.nd; ++q)
               if (!(taken & (1u << q))) { li = q; break; }
@@ -278,9 +399,10 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
             bidx[eoff + 32 * k + l] = (unsigned short)li;
           }
         }
+      }
       eoff += 32 * w;
     }
-    for (int j = 0; j < c.nr; ++j) NM_REQUIRE(rem[j].empty(), "slab: row longer than its lanes");
+    NM_REQUIRE((long long)slot_src.size() - nslot_before == (long long)chunk_entries, "slab: entries lost while scheduling");
     NM_REQUIRE(eoff == nep, "slab: padded entry count mismatch");
     for (int j = 0; j < c.nd; ++j) lidx_of[cols[j]] = -1;
   }
@@ -380,7 +502,7 @@ void nm_slab_build_into(NmParcsr& M, NmSlab& S, const std::vector<int>& rp, cons
 // and CTA assignment) to form y = A x in pack order.  Returns the pack order and geometry for the caller to check.
 extern "C" int nm_slab_host_selftest(int n, int ncolb, int R, const int* rp_, const int* idx_, const double* vals,
                                      const double* x /* R*ncolb */, double* y /* R*n, pack order */, int* order_out,
-                                     int* info /* 8: nchunk, grid, threads, smem_bytes, nstage, max_chunks_per_cta, padded, sum nd */) {
+                                     int* info /* 10: nchunk, grid, threads, smem_bytes, nstage, max_chunks_per_cta, padded, sum nd, x wavefronts (model), ideal */) {
   NM_API_BEGIN
   std::vector<int> rp(rp_, rp_ + n + 1), idx(idx_, idx_ + rp_[n]);
   NmSlabHost H;
@@ -391,6 +513,7 @@ extern "C" int nm_slab_host_selftest(int n, int ncolb, int R, const int* rp_, co
   for (int i = 0; i < n; ++i) newid[H.order[i]] = i;
   std::vector<char> seen(n, 0);
   std::vector<double> xs;
+  long long model_wavefronts = 0, model_ideal = 0;
   for (int g = 0; g < H.grid; ++g) {
     NM_REQUIRE(H.cta_first[g + 1] - H.cta_first[g] >= 1 && H.cta_first[g + 1] - H.cta_first[g] <= std::min(NM_SLAB_MAXDESC, H.threads),
                "slab: CTA %d has %d chunks", g, H.cta_first[g + 1] - H.cta_first[g]);
@@ -425,6 +548,19 @@ extern "C" int nm_slab_host_selftest(int n, int ncolb, int R, const int* rp_, co
           if (warp < h.nslice) {
             const unsigned eoff = tbl[2 * warp], w = tbl[2 * warp + 1];
             for (unsigned k = 0; k < w; ++k) {
+              if (lane == 0 || lane == 16) {
+                // modelled shared-memory wavefronts of one x component read by this half-warp at this step: 8-byte
+                // accesses, 16 bank pairs; lanes reading the same address share a wavefront
+                int cnt[16] = {0}, seen_li[16][16], nseen[16] = {0}, worst = 1;
+                for (int l2 = lane; l2 < lane + 16; ++l2) {
+                  const int li2 = sidx[eoff + 32 * k + l2], bp = (R * li2) & 15;
+                  bool dup = false;
+                  for (int q = 0; q < nseen[bp]; ++q) dup = dup || seen_li[bp][q] == li2;
+                  if (!dup) { seen_li[bp][nseen[bp]++] = li2; cnt[bp]++; worst = std::max(worst, cnt[bp]); }
+                }
+                model_wavefronts += worst;
+                model_ideal += 1;
+              }
               const double m = sv[eoff + 32 * k + lane];
               const int li = sidx[eoff + 32 * k + lane];
               NM_REQUIRE(li < h.nd, "slab: local index");
@@ -464,6 +600,8 @@ extern "C" int nm_slab_host_selftest(int n, int ncolb, int R, const int* rp_, co
     long long snd = 0;
     for (int ci = 0; ci < H.nchunk; ++ci) snd += ((const NmSlabHeader*)(H.blob.data() + 16ull * H.desc[ci].off16))->nd;
     info[7] = (int)std::min<long long>(snd, 0x7fffffff);                     // sum of distinct columns over chunks
+    info[8] = (int)std::min<long long>(model_wavefronts, 0x7fffffff);        // modelled wavefronts of one x component
+    info[9] = (int)std::min<long long>(model_ideal, 0x7fffffff);             // ... and the conflict-free count
   }
   NM_API_END
 }

@@ -16,9 +16,9 @@ def _selftest(S, R, x, ncolb=None):
     n = S.shape[0]
     ncolb = ncolb or S.shape[1]
     rp, idx, vals = i32(S.indptr), i32(S.indices), f64(S.data)
-    y = np.full(R * n, np.nan); order = np.empty(n, dtype=np.int32); info = np.zeros(8, dtype=np.int32)
+    y = np.full(R * n, np.nan); order = np.empty(n, dtype=np.int32); info = np.zeros(10, dtype=np.int32)
     check(lib().nm_slab_host_selftest(n, ncolb, R, iptr(rp), iptr(idx), dptr(vals), dptr(f64(x)), dptr(y), iptr(order), iptr(info)))
-    return y, order, dict(zip(("nchunk", "grid", "threads", "smem", "nstage", "maxper", "padded", "sum_nd"), info.tolist()))
+    return y, order, dict(zip(("nchunk", "grid", "threads", "smem", "nstage", "maxper", "padded", "sum_nd", "x_wavefronts", "x_ideal"), info.tolist()))
 
 
 CONFIGS = [dict(), dict(NM_SLAB_THREADS="64"), dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="8"),
@@ -56,6 +56,8 @@ def test_slab_pack_walk_equals_csr_product(monkeypatch, cfg):
         assert info["padded"] >= nnz
         if not cfg:
             assert info["padded"] <= 1.5 * nnz, info          # padding stays bounded (warps hold lanes of similar length)
+            # modelled shared-memory wavefronts of the x reads against the conflict-free count (share-aware schedule)
+            assert info["x_wavefronts"] <= 1.45 * info["x_ideal"], info
 
 
 def test_slab_pack_with_ghost_columns(monkeypatch):
