@@ -60,9 +60,77 @@ static void cheb_build_ppack(NmChebIter& C) {
     NM_CUDA(cudaMemcpy(order.data(), order_dev, n * sizeof(int), cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; ++i) newid[order[i]] = i;
     M.halo.send_idx.download(sidx.data(), sidx.size());
+    // fused multi-GPU step (opt-in): every sent row must sit in a chunk that polls the arrival flags before it is
+    // walked, i.e. the row itself must reference a ghost column (true for the symmetric B~ / Ap~)
+    bool fused = nm_env_int("NM_HALO_FUSED", 0) != 0 && C.pslab.nchunk > 0 && C.pslab.ws && M.halo.p2p;
+    if (fused)
+      for (int v : sidx) {
+        const int row = v / R;
+        bool ghost = false;
+        for (int p = rp[row]; p < rp[row + 1] && !ghost; ++p) ghost = idx[p] >= n;
+        if (!ghost) { fused = false; break; }
+      }
     for (int& v : sidx) v = R * newid[v / R] + v % R;
     C.send_idx_p.from_host(sidx);
+    if (fused) {
+      const int P = nm_ctx().nranks;
+      std::vector<int> cnt(n + 1, 0);
+      for (int v : sidx) cnt[v / R + 1]++;
+      for (int i = 0; i < n; ++i) cnt[i + 1] += cnt[i];
+      std::vector<NmPushEnt> ent(sidx.size());
+      std::vector<int> fill(cnt.begin(), cnt.end() - 1);
+      for (int r = 0; r < P; ++r)
+        for (int i = M.halo.send_off[r]; i < M.halo.send_off[r + 1]; ++i) {
+          const int v = sidx[i];
+          NmPushEnt e;
+          e.dst = (unsigned)(M.halo.peer_base[r] + (i - M.halo.send_off[r]));
+          e.peer = (unsigned short)r; e.comp = (unsigned short)(v % R);
+          ent[fill[v / R]++] = e;
+        }
+      C.push_off.from_host(cnt);
+      C.push_ent.alloc(std::max<size_t>(ent.size(), 1)); C.push_ent.upload(ent.data(), ent.size());
+      C.fused = true;
+    }
   }
+}
+
+// One step of the fused multi-GPU iteration: kernel k polls the flags of the values it gathers (pushed by the peers'
+// step k-1, or by the explicit push of b before step 0) and stores its own new direction into the peers' windows.
+static void cheb_step_fused(NmChebIter& C, const double* din, const EpiCheb& e, int k, NmHaloWait& poll) {
+  NmParcsr& M = *C.M;
+  NmHalo& h = M.halo;
+  NmCtx& c = nm_ctx();
+  if (k == 0) {
+    const bool ok = nm_halo_push_nowait(M, din, C.send_idx_p.p, &poll);
+    NM_REQUIRE(ok, "fused step without a peer window");
+  }
+  NmSlabFusedArgs F;
+  memset(&F, 0, sizeof(F));
+  NmHaloWait next;
+  next.flags = nullptr; next.mask = 0; next.epoch = 0; next.status = nullptr;
+  double* next_xg = nullptr;
+  if (k < C.deg - 1) {
+    const unsigned long long epoch = ++h.epoch;
+    const int par = (int)(epoch & 1);
+    F.push_off = C.push_off.p; F.push_ent = C.push_ent.p;
+    for (int r = 0; r < c.nranks; ++r) {
+      if (r == c.rank) continue;
+      if (h.send_cnt[r] > 0) {
+        F.send_mask |= 1u << r;
+        F.peer_xg[r] = (double*)(c.peer_win[r] + h.peer_xg[par][r]);      // NmPushEnt::dst already includes peer_base
+        F.peer_flag[r] = (unsigned long long*)(c.peer_win[r] + h.peer_flag[r]) + c.rank;
+      }
+      if (h.recv_cnt[r] > 0) next.mask |= 1u << r;
+    }
+    F.push_epoch = epoch;
+    F.ctr = c.push_ctr + 8;
+    next.flags = (const unsigned long long*)(c.win + h.win_flag);
+    next.epoch = epoch; next.status = c.dev_status;
+    next_xg = (double*)(c.win + h.win_xg[par]);
+  }
+  nm_slabws_dispatch<true>(M, C.pslab, din, e, poll, F);
+  if (next_xg) h.xg_cur = next_xg;
+  poll = next;
 }
 
 NmChebIter* nm_chebiter_build(double lb, double ub, int deg, NmParcsr* M) {
@@ -107,6 +175,8 @@ void nm_chebiter_solve(NmChebIter& C, const double* b, double* x) {
     x = C.xp.p;
   }
   const double* din = b;
+  NmHaloWait fused_poll;
+  fused_poll.flags = nullptr; fused_poll.mask = 0; fused_poll.epoch = 0; fused_poll.status = nullptr;
   for (int k = 0; k < C.deg; ++k) {
     EpiCheb e;
     e.first = (k == 0); e.last = (k == C.deg - 1);
@@ -116,7 +186,8 @@ void nm_chebiter_solve(NmChebIter& C, const double* b, double* x) {
     e.d_out = dbuf[k & 1];
     e.x = x;
     e.inv_theta = 1.0 / C.theta; e.ak = C.ak[k]; e.bk = C.bk[k];
-    if (C.pslab.nchunk > 0) nm_spmv_slab_epi(M, C.pslab, din, e, C.send_idx_p.p);
+    if (C.fused) cheb_step_fused(C, din, e, k, fused_poll);
+    else if (C.pslab.nchunk > 0) nm_spmv_slab_epi(M, C.pslab, din, e, C.send_idx_p.p);
     else if (C.psell.nchunk > 0) nm_spmv_sell_epi(M, C.psell, din, e, C.send_idx_p.p);
     else if (perm) nm_spmv_pack_epi(M, C.ppack, din, e, C.send_idx_p.p);
     else nm_spmv_epi(M, din, e);

@@ -223,6 +223,9 @@ struct NmParcsr {
   long long fmt_bytes = 0;                // bytes one SpMV streams in the chosen format (matrix part)
 };
 
+// fused multi-GPU step (nm_slab.cuh): where the new direction of a boundary row goes
+struct NmPushEnt { unsigned dst; unsigned short peer, comp; };   // position in that peer's ghost buffer, peer rank, scalar component
+
 // ---------------------------------------------------------------- ChebIter (B^-1, Ap^-1)
 struct NmChebIter {
   NmParcsr* M = nullptr;
@@ -237,6 +240,10 @@ struct NmChebIter {
   long long ppack_version = -1;
   DBuf<double> bp, xp;                    // b and x in pack order
   DBuf<int> send_idx_p;                   // halo send list in pack order
+  // NM_HALO_FUSED=1 (off by default): per pack-order index row the peer stores of its new direction
+  bool fused = false;
+  DBuf<int> push_off;
+  DBuf<NmPushEnt> push_ent;
   long long nsolve = 0, nmatvec = 0;
   double t_total = 0;
 };

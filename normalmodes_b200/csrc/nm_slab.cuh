@@ -223,6 +223,21 @@ struct NmSlabWsArgs {
   int ghost_cg;             // 1: read ghost values with ld.global.cg (synchronous); 0: cp.async like the owned ones
 };
 
+// Fused multi-GPU step (NM_HALO_FUSED=1, off by default -- written after the round's last GPU run, to be validated
+// first thing next round): no kernel between two steps.  The first lane of a boundary row stores its new direction
+// straight into the peers' ghost buffers (NVLink peer window) from the epilogue; every consumer warp fences its peer
+// stores and counts itself done; the grid's last warp raises this rank's arrival flag in every destination window.
+// The next step polls the flags before its first chunk with ghost columns, as in the overlapped exchange.
+struct NmSlabFusedArgs {
+  const int* push_off;          // per pack-order index row: [off, off') into push_ent; null = nothing to push
+  const NmPushEnt* push_ent;    // peer, scalar component, position in that peer's ghost buffer
+  double* peer_xg[8];           // this rank's block in each peer's ghost buffer (parity of push_epoch applied)
+  unsigned long long* peer_flag[8];
+  unsigned send_mask;
+  unsigned long long push_epoch;
+  unsigned* ctr;                // consumer warps done (device counter, reset by the last one)
+};
+
 // ghost values were written by a peer GPU during this kernel's lifetime: read them through L2 (no L1 allocation)
 __device__ __forceinline__ double nm_ld_cg(const double* p) {
   double v;
@@ -242,8 +257,8 @@ __device__ __forceinline__ void nm_slab_gather_ghost(const NmSlabView& v, double
   __threadfence_block();                                         // the plain stores above precede the barrier arrival
 }
 
-template <int R, int NC, class Epi>
-__global__ void __launch_bounds__(32 * (NC + 8)) k_slabws(NmSlabWsArgs W, Epi epi) {
+template <int R, int NC, bool FUSED, class Epi>
+__global__ void __launch_bounds__(32 * (NC + 8)) k_slabws(NmSlabWsArgs W, Epi epi, NmSlabFusedArgs F) {
   const NmSlabArgs& A = W.a;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -382,14 +397,47 @@ __global__ void __launch_bounds__(32 * (NC + 8)) k_slabws(NmSlabWsArgs W, Epi ep
       }
     }
     if (own) {
+      if constexpr (FUSED) {
+        double dn[R];
 #pragma unroll
-      for (int c = 0; c < R; ++c) epi.apply(row0 + c, acc[c], in[c]);
+        for (int c = 0; c < R; ++c) dn[c] = epi.apply_dn(row0 + c, acc[c], in[c]);
+        if (F.push_off) {
+          const int prow = v.h.first + (int)(lw & 0x3ffu);
+          for (int e = F.push_off[prow]; e < F.push_off[prow + 1]; ++e) {
+            const NmPushEnt pe = F.push_ent[e];
+            double val = dn[0];
+#pragma unroll
+            for (int c = 1; c < R; ++c) if (pe.comp == c) val = dn[c];
+            F.peer_xg[pe.peer][pe.dst] = val;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < R; ++c) epi.apply(row0 + c, acc[c], in[c]);
+      }
+    }
+  }
+  if constexpr (FUSED) {
+    if (F.push_off) {
+      __syncwarp();                                               // the warp's peer stores happen-before lane 0's fence
+      if (lane == 0) {
+        __threadfence_system();
+        const unsigned total = gridDim.x * NC;
+        if (atomicAdd(F.ctr, 1u) == total - 1) {                  // last consumer warp of the grid: every store is ordered
+          __threadfence_system();
+          for (int r = 0; r < 8; ++r)
+            if (F.send_mask & (1u << r))
+              asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(F.peer_flag[r]), "l"(F.push_epoch) : "memory");
+          *F.ctr = 0;
+        }
+      }
     }
   }
 }
 
-template <int R, int NC, class Epi>
-static inline void nm_slabws_launch_t(NmParcsr& M, NmSlab& S, const double* x, const Epi& epi, const NmHaloWait& hw) {
+template <int R, int NC, bool FUSED, class Epi>
+static inline void nm_slabws_launch_t(NmParcsr& M, NmSlab& S, const double* x, const Epi& epi, const NmHaloWait& hw,
+                                      const NmSlabFusedArgs& F) {
   NmCtx& c = nm_ctx();
   NmSlabWsArgs W;
   NmSlabArgs& A = W.a;
@@ -403,7 +451,7 @@ static inline void nm_slabws_launch_t(NmParcsr& M, NmSlab& S, const double* x, c
   W.ghost_cg = ghost_cg;
   static bool attr_set = false;                                  // per template instantiation
   if (!attr_set) {
-    NM_CUDA(cudaFuncSetAttribute(k_slabws<R, NC, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    NM_CUDA(cudaFuncSetAttribute(k_slabws<R, NC, FUSED, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
@@ -413,7 +461,7 @@ static inline void nm_slabws_launch_t(NmParcsr& M, NmSlab& S, const double* x, c
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = S.pdl ? 1 : 0;
-  NM_CUDA(cudaLaunchKernelEx(&cfg, k_slabws<R, NC, Epi>, W, epi));
+  NM_CUDA(cudaLaunchKernelEx(&cfg, k_slabws<R, NC, FUSED, Epi>, W, epi, F));
   c.launches++;
 }
 
@@ -434,6 +482,21 @@ static inline void nm_slab_launch_t(NmParcsr& M, NmSlab& S, const double* x, con
   c.launches++;
 }
 
+template <bool FUSED, class Epi>
+static inline void nm_slabws_dispatch(NmParcsr& M, NmSlab& S, const double* x, const Epi& epi, const NmHaloWait& hw,
+                                      const NmSlabFusedArgs& F) {
+  const bool blk = M.format == NM_FMT_KRON3;
+  if (S.threads == 512) {
+    if (blk) nm_slabws_launch_t<3, 16, FUSED, Epi>(M, S, x, epi, hw, F); else nm_slabws_launch_t<1, 16, FUSED, Epi>(M, S, x, epi, hw, F);
+  } else if (S.threads == 256) {
+    if (blk) nm_slabws_launch_t<3, 8, FUSED, Epi>(M, S, x, epi, hw, F); else nm_slabws_launch_t<1, 8, FUSED, Epi>(M, S, x, epi, hw, F);
+  } else if (S.threads == 64) {
+    if (blk) nm_slabws_launch_t<3, 2, FUSED, Epi>(M, S, x, epi, hw, F); else nm_slabws_launch_t<1, 2, FUSED, Epi>(M, S, x, epi, hw, F);
+  } else {
+    if (blk) nm_slabws_launch_t<3, 4, FUSED, Epi>(M, S, x, epi, hw, F); else nm_slabws_launch_t<1, 4, FUSED, Epi>(M, S, x, epi, hw, F);
+  }
+}
+
 // Product through the slabs: x and the epilogue vectors are in pack order (S.order).
 template <class Epi>
 static inline void nm_spmv_slab_epi(NmParcsr& M, NmSlab& S, const double* x, const Epi& epi, const int* send_idx) {
@@ -447,15 +510,9 @@ static inline void nm_spmv_slab_epi(NmParcsr& M, NmSlab& S, const double* x, con
       nm_halo_exchange(M, x, send_idx);
       hw.flags = nullptr; hw.mask = 0; hw.epoch = 0; hw.status = nullptr;
     }
-    if (S.threads == 512) {
-      if (blk) nm_slabws_launch_t<3, 16, Epi>(M, S, x, epi, hw); else nm_slabws_launch_t<1, 16, Epi>(M, S, x, epi, hw);
-    } else if (S.threads == 256) {
-      if (blk) nm_slabws_launch_t<3, 8, Epi>(M, S, x, epi, hw); else nm_slabws_launch_t<1, 8, Epi>(M, S, x, epi, hw);
-    } else if (S.threads == 64) {
-      if (blk) nm_slabws_launch_t<3, 2, Epi>(M, S, x, epi, hw); else nm_slabws_launch_t<1, 2, Epi>(M, S, x, epi, hw);
-    } else {
-      if (blk) nm_slabws_launch_t<3, 4, Epi>(M, S, x, epi, hw); else nm_slabws_launch_t<1, 4, Epi>(M, S, x, epi, hw);
-    }
+    NmSlabFusedArgs F;
+    memset(&F, 0, sizeof(F));
+    nm_slabws_dispatch<false>(M, S, x, epi, hw, F);
     return;
   }
   nm_halo_exchange(M, x, send_idx);

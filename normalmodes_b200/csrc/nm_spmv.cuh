@@ -109,6 +109,30 @@ struct EpiCheb {
       d_out[row] = dn;
     }
   }
+  // same update, returning the new direction d_out[row] (what the next step gathers): used by the fused multi-GPU
+  // step, which stores it straight into the peers' ghost buffers
+  __device__ __forceinline__ double apply_dn(int row, double acc, const In& in) const {
+    double d, rn, xn;
+    if (first) {
+      const double b = in.r;
+      d = b * inv_theta;
+      rn = b - acc * inv_theta;
+      xn = d;
+    } else {
+      d = in.d;
+      rn = in.r - acc;
+      xn = in.x + d;
+    }
+    const double dn = ak * d + bk * rn;
+    if (last) {
+      x[row] = xn + dn;
+    } else {
+      x[row] = xn;
+      r_out[row] = rn;
+      d_out[row] = dn;
+    }
+    return dn;
+  }
 };
 // ChebAv three-term update fused with the A product (u = A w [+ add]):
 //   v+ = t*(u - cc*vk) - vkm1 ; y (+)= mu*v+ ; vout may alias vkm1 (only this row reads it)

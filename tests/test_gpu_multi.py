@@ -44,3 +44,11 @@ def test_two_ranks_blocking_exchange_and_nccl_fallback(env):
 def test_all_ranks_halo_exchange_and_solve():
     out = _run(min(_ngpu(), 8), 29613, env_extra={"NM_MP_CASES": "prem3k_p1_j2"})
     print(out[-1500:])
+
+
+@pytest.mark.skipif(_ngpu() < 2 or os.environ.get("NM_TEST_FUSED") != "1",
+                    reason="needs >= 2 GPUs and NM_TEST_FUSED=1 (fused step: written after round 1's last GPU run, not validated yet)")
+def test_two_ranks_fused_step():
+    """NM_HALO_FUSED=1: boundary rows stored to the peers from the step kernel's epilogue, no kernel between steps."""
+    out = _run(2, 29617, env_extra=dict(NM_HALO_FUSED="1"))
+    print(out[-800:])
