@@ -139,6 +139,10 @@ int nm_pevsl_stats(void* pevsl, int* steps, int* deg, double* t_total, double* t
 /* one application y = p(A B^-1) z of the polynomial filter (ChebAv), the unit of the headline metric */
 int nm_pevsl_filter_host(void* pevsl, void* pol, const double* z, double* y);
 int nm_pevsl_filter_dev(void* pevsl, void* pol, const double* z_dev, double* y_dev, double* work3n_dev);
+/* the same sum truncated after kmax degree steps (kmax <= 0: the whole polynomial): a fixed-size slice of one
+ * application, the unit bench.py times on meshes where a whole application takes minutes */
+int nm_pevsl_filter_steps_host(void* pevsl, void* pol, int kmax, const double* z, double* y);
+int nm_pevsl_filter_steps_dev(void* pevsl, void* pol, int kmax, const double* z_dev, double* y_dev, double* work3n_dev);
 
 #ifdef __cplusplus
 }

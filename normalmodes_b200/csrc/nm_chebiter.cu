@@ -115,12 +115,12 @@ static void cheb_step_fused(NmChebIter& C, const double* din, const EpiCheb& e, 
     F.push_off = C.push_off.p; F.push_ent = C.push_ent.p;
     for (int r = 0; r < c.nranks; ++r) {
       if (r == c.rank) continue;
-      if (h.send_cnt[r] > 0) {
+      if (h.send_cnt[r] > 0) F.peer_xg[r] = (double*)(c.peer_win[r] + h.peer_xg[par][r]);   // NmPushEnt::dst already includes peer_base
+      if (h.send_cnt[r] > 0 || h.recv_cnt[r] > 0) {                       // flags both ways on every link (nm_parcsr.cu)
         F.send_mask |= 1u << r;
-        F.peer_xg[r] = (double*)(c.peer_win[r] + h.peer_xg[par][r]);      // NmPushEnt::dst already includes peer_base
         F.peer_flag[r] = (unsigned long long*)(c.peer_win[r] + h.peer_flag[r]) + c.rank;
+        next.mask |= 1u << r;
       }
-      if (h.recv_cnt[r] > 0) next.mask |= 1u << r;
     }
     F.push_epoch = epoch;
     F.ctr = c.push_ctr + 8;

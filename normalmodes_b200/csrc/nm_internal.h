@@ -291,6 +291,7 @@ struct NmPevsl {
   long long n_filter_apply = 0;
   unsigned long long seed = 4321;
   double ritz_tol = 0.0;                   // > 0: per-pair residual-estimate gate on top of the trace test
+  DBuf<double> fwork;                      // device scratch of the host-vector filter entry points (5n)
 };
 
 // ---------------------------------------------------------------- internal entry points
@@ -350,6 +351,6 @@ void nm_findpol(const double xintv[4], double thresh_int, double thresh_ext, NmP
 // solver
 void nm_lanbounds(NmPevsl& P, int mlan, int lanstep, double tol, double* lmin, double* lmax);
 void nm_cheblannr(NmPevsl& P, const double xintv[4], int maxit, double tol, const NmPol& pol);
-void nm_filter_apply(NmPevsl& P, const NmPol& pol, const double* z, double* y, double* work /* 3n */);
+void nm_filter_apply(NmPevsl& P, const NmPol& pol, const double* z, double* y, double* work /* 3n */, int kmax = 0);
 
 static inline int nm_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -560,3 +560,23 @@ extern "C" int nm_pevsl_filter_dev(void* h, void* pol, const double* z_dev, doub
   nm_filter_apply(*(NmPevsl*)h, *(NmPol*)pol, z_dev, y_dev, work_dev);
   NM_API_END
 }
+// The same, truncated after kmax degree steps: y = sum_{k<=kmax} mu_k T_k((A B^-1 - c)/d) z (kmax <= 0: all of them).
+extern "C" int nm_pevsl_filter_steps_host(void* h, void* pol, int kmax, const double* z, double* y) {
+  NM_API_BEGIN
+  NmPevsl& P = *(NmPevsl*)h;
+  NmCtx& ctx = nm_ctx();
+  const size_t n = P.n;
+  if (P.fwork.n < 5 * std::max<size_t>(n, 1)) P.fwork.alloc(5 * std::max<size_t>(n, 1));
+  double* dz = P.fwork.p; double* dy = dz + n; double* work = dy + n;
+  if (n) NM_CUDA(cudaMemcpyAsync(dz, z, n * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  nm_filter_apply(P, *(NmPol*)pol, dz, dy, work, kmax);
+  if (n) NM_CUDA(cudaMemcpyAsync(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  NM_CUDA(cudaStreamSynchronize(ctx.stream));
+  nm_check_device_status();
+  NM_API_END
+}
+extern "C" int nm_pevsl_filter_steps_dev(void* h, void* pol, int kmax, const double* z_dev, double* y_dev, double* work_dev) {
+  NM_API_BEGIN
+  nm_filter_apply(*(NmPevsl*)h, *(NmPol*)pol, z_dev, y_dev, work_dev, kmax);
+  NM_API_END
+}

@@ -95,7 +95,7 @@ void nm_op_apply_filter(NmOp& op, const double* w, const double* vk, const doubl
 
 // ---------------------------------------------------------------- ChebAv
 // y = sum_k mu_k T_k((A B^-1 - cc)/dd) z.  work: 3n doubles (two recurrence vectors + w = B^-1 vk).
-void nm_filter_apply(NmPevsl& P, const NmPol& pol, const double* z, double* y, double* work) {
+void nm_filter_apply(NmPevsl& P, const NmPol& pol, const double* z, double* y, double* work, int kmax) {
   const size_t n = P.n;
   NM_REQUIRE(P.A, "filter: no A operator registered");
   double* va = work;
@@ -103,8 +103,10 @@ void nm_filter_apply(NmPevsl& P, const NmPol& pol, const double* z, double* y, d
   double* w = work + 2 * n;
   const double* vk = z;          // v_1 = z is only read
   const double* vkm1 = nullptr;  // v_0 = 0
-  const int m = pol.deg;
-  NM_REQUIRE(m >= 1, "filter: polynomial degree %d < 1", m);
+  NM_REQUIRE(pol.deg >= 1, "filter: polynomial degree %d < 1", pol.deg);
+  // kmax > 0: the sum truncated after kmax degree steps (a slice of one application: the unit bench.py times on
+  // meshes where a whole application takes minutes); every degree step costs the same
+  const int m = (kmax > 0 && kmax < pol.deg) ? kmax : pol.deg;
   for (int k = 1; k <= m; ++k) {
     // output slot: k=1 -> va, k=2 -> vb (v_{k-1} = z must survive), then in place over v_{k-1}
     double* vout = (k == 1) ? va : (k == 2 ? vb : const_cast<double*>(vkm1));
@@ -118,7 +120,7 @@ void nm_filter_apply(NmPevsl& P, const NmPol& pol, const double* z, double* y, d
     nm_op_apply_filter(*P.A, src, vk, vkm1, vout, y, t, pol.cc, pol.mu[k], pol.mu[0], k == 1);
     vkm1 = vk; vk = vout;
   }
-  P.n_filter_apply++;
+  if (m == pol.deg) P.n_filter_apply++;
 }
 
 // ---------------------------------------------------------------- C ABI: operators

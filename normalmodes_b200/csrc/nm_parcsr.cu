@@ -78,14 +78,18 @@ static void halo_push_launch(NmParcsr& M, const double* x, const int* send_idx, 
   A.recv_mask = A.send_mask = 0;
   for (int r = 0; r < 8; ++r) { A.peer_xg[r] = nullptr; A.peer_flag[r] = nullptr; }
   for (int r = 0; r <= 8; ++r) A.send_off[r] = r <= c.nranks ? h.send_off[std::min(r, c.nranks)] : h.nsend;
+  // Flags travel in BOTH directions of every link, also where values travel in one only (rectangular E / ET: a rank
+  // may send to a peer it receives nothing from): the receiver's flag is then a zero-length acknowledgement that its
+  // previous product is done, which is what bounds a sender to one exchange ahead of the slowest reader of the
+  // parity buffer it is about to overwrite.
   for (int r = 0; r < c.nranks; ++r) {
     if (r == c.rank) continue;
-    if (h.send_cnt[r] > 0) {
+    if (h.send_cnt[r] > 0) A.peer_xg[r] = (double*)(c.peer_win[r] + h.peer_xg[par][r]) + h.peer_base[r];
+    if (h.send_cnt[r] > 0 || h.recv_cnt[r] > 0) {
       A.send_mask |= 1u << r;
-      A.peer_xg[r] = (double*)(c.peer_win[r] + h.peer_xg[par][r]) + h.peer_base[r];
+      A.recv_mask |= 1u << r;
       A.peer_flag[r] = (unsigned long long*)(c.peer_win[r] + h.peer_flag[r]) + c.rank;
     }
-    if (h.recv_cnt[r] > 0) A.recv_mask |= 1u << r;
   }
   A.my_flag = (const unsigned long long*)(c.win + h.win_flag);
   A.epoch = epoch; A.ctr = c.push_ctr; A.status = c.dev_status; A.wait = wait;

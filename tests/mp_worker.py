@@ -16,6 +16,38 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def one_directional_halo(L, rank, nranks, torch):
+    """Block upper-triangular rectangular matrix: rank r gathers columns of the ranks > r only, so the last rank sends
+    and never receives (no arrival flag of its own to wait for).  60 products are queued back to back without a host
+    sync: without an acknowledgement from the readers the sender would overwrite a parity buffer still being read."""
+    import scipy.sparse as sp
+    from normalmodes_b200 import _lib, matvec as mv
+    nr, nc = 300, 4000                                              # rows / columns per rank
+    S = sp.random(nr * nranks, nc * nranks, density=0.02, random_state=5, format="lil")
+    for r in range(nranks):
+        S[r * nr:(r + 1) * nr, :r * nc] = 0
+    S = S.tocsr(); S.sort_indices()
+    loc = S[rank * nr:(rank + 1) * nr]
+    m = mv.COOmat([nr * r for r in range(nranks + 1)], loc.indptr, loc.indices, loc.data,
+                  coldist=[nc * r for r in range(nranks + 1)])
+    h = mv.parcsr_create(m)
+    reps = 60
+    xs = np.random.default_rng(3).uniform(-1, 1, (reps, nc * nranks))
+    xd = torch.from_numpy(np.ascontiguousarray(xs[:, rank * nc:(rank + 1) * nc])).cuda()
+    yd = torch.zeros(reps, nr, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    for k in range(reps):
+        _lib.check(L.nm_parcsr_matvec_dev(h, C.c_void_p(xd[k].data_ptr()), C.c_void_p(yd[k].data_ptr())))
+    _lib.check(L.nm_sync())
+    got = yd.cpu().numpy()
+    for k in range(reps):
+        ref = (S @ xs[k])[rank * nr:(rank + 1) * nr]
+        assert np.abs(got[k] - ref).max() <= 1e-12 * (np.abs(ref).max() + 1.0), ("one-directional halo", rank, k)
+    _lib.check(L.nm_parcsr_free(h))
+    if rank == 0:
+        print("MP one-directional halo ok on %d ranks" % nranks, flush=True)
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -106,6 +138,7 @@ def main():
         if rank == 0:
             print("MP case %s ok on %d ranks: %d eigenpairs, %d Lanczos steps" % (name, nranks, r.nev, r.steps), flush=True)
         f.free()
+    one_directional_halo(L, rank, nranks, torch)
     dist.barrier()
     _lib.check(L.nm_comm_finalize())
     dist.destroy_process_group()
