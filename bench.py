@@ -1,20 +1,28 @@
-"""Benchmark of the hot path: one application y = p(A B^-1) z of the Chebyshev polynomial filter
-(pEVSL ChebAv inside pEVSL_CHEBLANNR_F90, src/mod_pevsl.f90:122) on a builder-generated PREM-like mesh.
+"""Benchmark of the hot path: the Chebyshev polynomial filter y = p(A B^-1) z (pEVSL ChebAv inside
+pEVSL_CHEBLANNR_F90, src/mod_pevsl.f90:122) on a builder-generated PREM-like mesh.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--ntet 200000] [--porder 2] [--solve]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--ntet 2000000] [--porder 2] [--degree-steps 128]
 
-A "step" is one filter application (degree m from find_pol for the band): m x { ChebIter B-solve
-(degB fused SpMV steps) + fluid Schur term (ET, degAp fused SpMV steps on Ap~, E) + A product fused with
-the three-term update }.  `value` = ALGORITHMIC bytes of one application (CSR, 8-byte values, 4-byte
-indices) / device time, inputs resident in HBM; `e2e` = the same through the C ABI with HOST
-vectors (H2D of z and D2H of y inside the timed region).  One JSON line on stdout (rank 0).
+Workload (BASELINE.json config 3): PREM-like ~2 M-tet mesh, JOB 2, pOrder 2, band 0.1-1.0 mHz.  One filter application
+on it is ~9000 degree steps of { ChebIter B-solve (degB fused SpMV steps) + fluid Schur term (ET, degAp fused SpMV steps
+on Ap~, E) + A product fused with the three-term update } = minutes, so a "step" is a FIXED SLICE of one application:
+the first --degree-steps degree steps (every degree step costs the same).  `value` = ALGORITHMIC bytes of that slice
+(CSR, 8-byte values, 4-byte indices, SURVEY.md 8d: what the reference's CSR path moves) / device time, inputs resident
+in HBM; `e2e` = the same through the C ABI with HOST vectors (H2D of z and D2H of y inside the timed region);
+`roofline` = the dominant kernel (fused ChebIter step on B~) on the bytes it actually streams in ITS format, against the
+measured HBM bandwidth; `application` = the same accounting for the whole degree step; `check` = the first degree
+steps of the same application, GPU against the oracle's C port on the host, on the bench matrices (all ranks gathered);
+`cpu_baseline` / `--impl reference` = the oracle's C/OpenMP port of the same loops on the box's host cores (the
+Fortran + MPI + pEVSL reference cannot be built in this image).  One JSON line on stdout (rank 0).
 """
 import argparse
 import ctypes as C
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -24,22 +32,25 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
-def parse():
+def parse(argv=None):
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--steps", type=int, default=5)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--ntet", type=int, default=200000)
+    p.add_argument("--ntet", type=int, default=2000000)
     p.add_argument("--porder", type=int, default=2)
     p.add_argument("--job", type=int, default=2)
     p.add_argument("--lowfreq", type=float, default=0.1)
     p.add_argument("--upfreq", type=float, default=1.0)
+    p.add_argument("--degree-steps", type=int, default=128,
+                   help="ChebAv degree steps per bench step (0: a whole filter application)")
+    p.add_argument("--check-steps", type=int, default=2, help="degree steps compared with the CPU oracle (0: no check)")
     p.add_argument("--solve", action="store_true", help="also run the full eigen-solve (time-to-all-eigenpairs)")
-    p.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
+    p.add_argument("--cpu-seconds", type=float, default=8.0, help="target CPU work of one cpu_baseline / reference sample")
     p.add_argument("--no-cpu", action="store_true")
-    p.add_argument("--e2e-steps", type=int, default=2, help="filter applications timed through the host-vector C ABI")
-    return p.parse_args()
+    p.add_argument("--e2e-steps", type=int, default=2, help="bench steps timed through the host-vector C ABI")
+    return p.parse_args(argv)
 
 
 def log(*a):
@@ -61,7 +72,7 @@ def filter_step_bytes(nnz, n):         # fused filter step: SpMV on w + v, v-, y
 
 
 def filter_bytes(sz, deg, degB, degAp):
-    """sz: dict of GLOBAL nnz/rows.  Bytes of one y = p(A B^-1) z."""
+    """sz: dict of GLOBAL nnz/rows.  Algorithmic bytes of `deg` degree steps of y = p(A B^-1) z."""
     per = degB * cheb_step_bytes(sz["nnzB"], sz["N"]) + filter_step_bytes(sz["nnzA"], sz["N"])
     if sz["fluid"]:
         per += degAp * cheb_step_bytes(sz["nnzAp"], sz["Np"])
@@ -103,6 +114,15 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------- workload construction (product path)
+def p2_node_count(mesh):
+    """nvert + number of distinct mesh edges (the P2 node count; src/mod_geometry.f90:428-689 adds one node per edge)."""
+    e = mesh["ele"]
+    pairs = np.concatenate([e[:, [i, j]] for i, j in ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))])
+    pairs.sort(axis=1)
+    key = pairs[:, 0].astype(np.int64) * (int(mesh["nvert"]) + 1) + pairs[:, 1]
+    return int(mesh["nvert"]) + int(np.unique(key).size)
+
+
 def build_workload(a, rank, nranks):
     from normalmodes_b200 import meshgen, partition
     from normalmodes_b200.create_matrix import Fem
@@ -112,11 +132,10 @@ def build_workload(a, rank, nranks):
     log("mesh: %d tets, %d vertices (%.1fs)" % (mesh["ntet"], mesh["nvert"], time.time() - t0))
     part = None
     if nranks > 1:
-        # topology with a trivial partition gives the node ids (P2 edge numbering depends on nproc only)
-        nn_probe = Fem(mesh, model["vs"], a.porder, nproc=1)
-        nn1 = nn_probe.nn
-        nn_probe.free()
+        # topology with a trivial partition gives the node ids (the P2 edge numbering depends on nproc only)
+        nn1 = mesh["nvert"] if a.porder == 1 else p2_node_count(mesh)
         f0 = Fem(mesh, model["vs"], a.porder, nproc=nranks, part=np.zeros(nn1, dtype=np.int32), rank=0)
+        assert f0.nn == nn1, (f0.nn, nn1)
         X = partition.node_coordinates(mesh, f0)
         f0.free()
         part = partition.rcb(X, nranks)
@@ -143,19 +162,75 @@ def gather_sizes(CGM, fem, nranks):
 
 
 # ---------------------------------------------------------------------------- CPU arm (oracle port; reference unbuildable here)
-def cpu_ops_from(CGM, mv, fluid):
-    """CpuOps over the SAME CSR arrays the GPU path uses (B~ / Ap~ values read back from the device)."""
-    from oracle import cpu as ocpu
+def local_cpu_arrays(CGM, mv, fluid):
+    """This rank's rows of the matrices the CPU arm multiplies by: B~ / Ap~ values read back from the device (the
+    Jacobi scaling ran there), Ad / E / ET unscaled with the scalings d, dp -- exactly the reference's operands."""
     from normalmodes_b200._lib import lib, check, dptr
     B = CGM["B"]
     Bv = np.empty(B.NNZ); check(lib().nm_parcsr_get_values(mv.sBV, dptr(Bv)))
     A = CGM["Ad" if fluid else "A"]
-    kw = {}
+    out = dict(B_ia=B.rowdist, B_ja=B.col, B_a=Bv, A_ia=A.rowdist, A_ja=A.col, A_a=A.val, d=B.diag)
     if fluid:
         Ap = CGM["Ap"]; Apv = np.empty(Ap.NNZ); check(lib().nm_parcsr_get_values(mv.sApV, dptr(Apv)))
-        kw = dict(E=(CGM["E"].rowdist, CGM["E"].col, CGM["E"].val), ET=(CGM["ET"].rowdist, CGM["ET"].col, CGM["ET"].val),
-                  Ap=(Ap.rowdist, Ap.col, Apv), dp=Ap.diag, boundsAp=mv.boundsAp, degAp=mv.degAp)
-    return ocpu.CpuOps((B.rowdist, B.col, Bv), (A.rowdist, A.col, A.val), B.diag, mv.boundsB, mv.degB, **kw)
+        out.update(E_ia=CGM["E"].rowdist, E_ja=CGM["E"].col, E_a=CGM["E"].val,
+                   ET_ia=CGM["ET"].rowdist, ET_ja=CGM["ET"].col, ET_a=CGM["ET"].val,
+                   Ap_ia=Ap.rowdist, Ap_ja=Ap.col, Ap_a=Apv, dp=Ap.diag)
+    return out
+
+
+def cpu_ops_from_arrays(parts, mv, fluid):
+    """CpuOps over the GLOBAL matrices: the ranks' row blocks (global 0-based column ids already) stacked in rank order."""
+    from oracle import cpu as ocpu
+
+    def stack(name):
+        ia = [np.asarray(p[name + "_ia"], dtype=np.int64) for p in parts]
+        off = np.cumsum([0] + [int(x[-1]) for x in ia])
+        gia = np.concatenate([ia[0]] + [x[1:] + off[i] for i, x in enumerate(ia) if i > 0]) if len(ia) > 1 else ia[0]
+        assert gia[-1] < 2 ** 31, "CPU oracle uses 32-bit row pointers"
+        return (gia.astype(np.int32), np.concatenate([p[name + "_ja"] for p in parts]) if len(parts) > 1 else parts[0][name + "_ja"],
+                np.concatenate([p[name + "_a"] for p in parts]) if len(parts) > 1 else parts[0][name + "_a"])
+    d = np.concatenate([p["d"] for p in parts])
+    kw = {}
+    if fluid:
+        kw = dict(E=stack("E"), ET=stack("ET"), Ap=stack("Ap"), dp=np.concatenate([p["dp"] for p in parts]),
+                  boundsAp=mv.boundsAp, degAp=mv.degAp)
+    return ocpu.CpuOps(stack("B"), stack("A"), d, mv.boundsB, mv.degB, **kw)
+
+
+def gather_cpu_ops(CGM, mv, fluid, rank, nranks):
+    """rank 0: CpuOps of the global problem.  Other ranks hand their blocks over through a node-local scratch
+    directory (one box: /dev/shm), not through the communicator -- these are gigabytes of test data."""
+    loc = local_cpu_arrays(CGM, mv, fluid)
+    if nranks == 1:
+        return cpu_ops_from_arrays([loc], mv, fluid)
+    import torch.distributed as dist
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    tag = [None]
+    if rank == 0:
+        tag[0] = tempfile.mkdtemp(prefix="nm_bench_", dir=base)
+    dist.broadcast_object_list(tag, src=0)
+    d = tag[0]
+    if rank != 0:
+        for k, v in loc.items():
+            np.save(os.path.join(d, "r%d_%s.npy" % (rank, k)), np.ascontiguousarray(v))
+    dist.barrier()
+    ops = None
+    if rank == 0:
+        parts = [loc] + [{k: np.load(os.path.join(d, "r%d_%s.npy" % (r, k))) for k in loc} for r in range(1, nranks)]
+        ops = cpu_ops_from_arrays(parts, mv, fluid)
+        shutil.rmtree(d, ignore_errors=True)
+    return ops
+
+
+def gather_vector(v_local, rank, nranks):
+    """Host copy of a distributed device vector on rank 0 (rank order = global row order)."""
+    h = v_local.detach().cpu().numpy()
+    if nranks == 1:
+        return h
+    import torch.distributed as dist
+    out = [None] * nranks if rank == 0 else None
+    dist.gather_object(h, out, dst=0)
+    return np.concatenate(out) if rank == 0 else None
 
 
 def time_cpu_sample(cops, pol, sz, degB, degAp, target_s, steps=1, warmup=0):
@@ -186,7 +261,6 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     from normalmodes_b200 import _lib, matvec as mvmod, pevsl
-    from normalmodes_b200.create_matrix import MAT_IDS  # noqa: F401
     L = _lib.lib()
     _lib.check(L.nm_init(local))
     use_dist = nranks > 1 and a.impl == "ours"
@@ -202,12 +276,14 @@ def main():
         _lib.check(L.nm_comm_init(rank, nranks, bytes(idbuf.cpu().numpy().tobytes())))
     nr = nranks if use_dist else 1
     rk = rank if use_dist else 0
+    t_start = time.time()
     mesh, model, fem = build_workload(a, rk, nr)
     t0 = time.time()
     fem.assemble(a.job, model)
     names = ("Ad", "B", "E", "ET", "Ap") if fem.fluidcase else ("A", "B")
     CGM = {k: fem.matrix(k) for k in names}
     t_asm = time.time() - t0
+    del model
     sz = gather_sizes(CGM, fem, nr)
     log("assembly (device) + copy-out: %.1fs; global nnz A %d, B %d" % (t_asm, sz["nnzA"], sz["nnzB"]))
     t0 = time.time()
@@ -222,22 +298,31 @@ def main():
     xintv = np.array([lo, up, LMIN, LMAX])
     pol = pevsl.Pol(xintv, 0.8, 0.7)
     degAp = mv.degAp if fem.fluidcase else 0
-    log("setupmatvec %.1fs, bounds of B^-1A [%.3e, %.3e] %.1fs, filter degree %d" % (t_setup, LMIN, LMAX, t_bounds, pol.deg))
-    nbytes = filter_bytes(sz, pol.deg, mv.degB, degAp)
-    workload = "PREM-like %d-tet mesh (builder-generated), JOB %d, pOrder %d, band %.2f-%.2f mHz, N=%d, nnz(A)=%d" % (
-        mesh["ntet"], a.job, a.porder, a.lowfreq, a.upfreq, sz["N"], sz["nnzA"])
-    config = dict(workload=workload, filter_degree=pol.deg, degB=mv.degB, degAp=degAp, ranks=nr,
-                  l2="matrices + vectors of one application exceed L2 (CSR %.0f MB); no flush between steps" % (
-                      (12 * (sz["nnzA"] + sz["nnzB"])) / 1e6))
+    D = pol.deg if a.degree_steps <= 0 else min(a.degree_steps, pol.deg)
+    log("setupmatvec %.1fs, bounds of B^-1A [%.3e, %.3e] %.1fs, filter degree %d, bench step = %d degree steps" % (
+        t_setup, LMIN, LMAX, t_bounds, pol.deg, D))
+    nbytes = filter_bytes(sz, D, mv.degB, degAp)
+    # `config` names the workload only (identical in both arms and for every N); measured / derived sizes go to `detail`
+    config = dict(workload="PREM-like %d-tet mesh (builder-generated, target %d), JOB %d, pOrder %d, band %.2f-%.2f mHz" % (
+                      mesh["ntet"], a.ntet, a.job, a.porder, a.lowfreq, a.upfreq),
+                  step="%s ChebAv degree steps of one filter application y = p(A B^-1) z; per degree step: %d fused ChebIter "
+                       "steps on B~, %d on Ap~, the ET / E products and the A product fused with the three-term update" % (
+                           "the first %d" % a.degree_steps if a.degree_steps > 0 else "all", mv.degB, degAp),
+                  degB=mv.degB, degAp=degAp,
+                  l2="every matrix of the degree step exceeds L2 at N=1; inputs are not flushed between steps (one step streams "
+                     "%.0f GB in the reference's CSR layout)" % (nbytes / 1e9))
+    detail = dict(N=sz["N"], Np=sz["Np"], nnzA=sz["nnzA"], nnzB=sz["nnzB"], nnzAp=sz.get("nnzAp", 0), nnzE=sz.get("nnzE", 0),
+                  filter_degree=pol.deg, degree_steps_per_step=D, ranks=nr, algorithmic_bytes_per_step=nbytes,
+                  spectrum=[LMIN, LMAX], interval=[lo, up])
 
     if a.impl == "reference":
         # The reference (Fortran + MPI + pEVSL + ParMETIS) cannot be built in this image: time the oracle's C/OpenMP
         # restatement of the same loops on the host cores, on the same matrices and polynomial.
-        cops = cpu_ops_from(CGM, mv, bool(fem.fluidcase))
+        cops = gather_cpu_ops(CGM, mv, bool(fem.fluidcase), 0, 1)
         cb, tm, kmax = time_cpu_sample(cops, pol, sz, mv.degB, degAp, a.cpu_seconds, steps=a.steps, warmup=min(a.warmup, 1))
         out = dict(metric="filtered_spmv_hbm_gbs", value=cb["value"], unit="GB/s", n_gpus=a.gpus, steps=a.steps,
                    warmup=a.warmup, ms_per_step=tm * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None,
-                   dtype="f64", data="synthetic", config=config, impl="reference", cpu_baseline=cb,
+                   dtype="f64", data="synthetic", config=config, detail=detail, impl="reference", cpu_baseline=cb,
                    e2e=dict(value=cb["value"], unit="GB/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
         print(json.dumps(out), flush=True)
         return
@@ -249,19 +334,47 @@ def main():
     y = torch.empty_like(z); work = torch.empty(3 * max(n, 1), dtype=torch.float64, device="cuda")
     torch.cuda.synchronize()
 
-    def step_dev():
-        _lib.check(L.nm_pevsl_filter_dev(P.h, pol.h, C.c_void_p(z.data_ptr()), C.c_void_p(y.data_ptr()), C.c_void_p(work.data_ptr())))
+    def step_dev(kmax=D):
+        _lib.check(L.nm_pevsl_filter_steps_dev(P.h, pol.h, int(kmax), C.c_void_p(z.data_ptr()), C.c_void_p(y.data_ptr()),
+                                               C.c_void_p(work.data_ptr())))
 
     def barrier():
         if use_dist:
             import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if not use_dist:
+            return ms
+        import torch.distributed as dist
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- check: the first degree steps of this very application, GPU against the CPU oracle, all ranks gathered
+    check = None
+    cops = None
+    if a.check_steps > 0 and not a.no_cpu:
+        t0 = time.time()
+        K = min(a.check_steps, pol.deg)
+        step_dev(K)
+        barrier()
+        yg = gather_vector(y, rk, nr); zg = gather_vector(z, rk, nr)
+        cops = gather_cpu_ops(CGM, mv, bool(fem.fluidcase), rk, nr)
+        if rank == 0:
+            yc = cops.chebav(pol.deg, pol.mu, pol.cc, pol.dd, zg, kmax=K)
+            err = float(np.abs(yg - yc).max() / np.abs(yc).max())
+            check = dict(max_rel_err=err, degree_steps=K, tol=1e-10, ok=bool(err <= 1e-10),
+                         against="oracle/c (C/OpenMP port of pEVSL ChebAv + ChebIter + sparsefsAV) on the host, same matrices and z, "
+                                 "%d rank(s) gathered" % nr)
+            log("check: %d degree steps, max |y_gpu - y_cpu| / max |y_cpu| = %.2e (%.1fs)" % (K, err, time.time() - t0))
+            assert err <= 1e-8, "bench check failed: GPU and CPU filter differ by %.2e" % err
+        barrier()
     tw = time.time()
     for _ in range(a.warmup):
         step_dev()
     barrier()
-    log("warm-up: %d filter applications, %.2f s each" % (a.warmup, (time.time() - tw) / max(a.warmup, 1)))
+    log("warm-up: %d steps, %.2f s each" % (a.warmup, (time.time() - tw) / max(a.warmup, 1)))
     l0 = L.nm_launch_count()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as cs:
@@ -272,20 +385,18 @@ def main():
         e1.record(stream)
         barrier()
         torch.cuda.profiler.stop()
-    ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(e0.elapsed_time(e1))
     launches = int(L.nm_launch_count() - l0)
-    if use_dist:
-        import torch.distributed as dist
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     ms_per_step = ms / a.steps
     value = nbytes / (ms_per_step * 1e-3) / 1e9
-    log("device-resident: %.1f ms per application, %.0f GB/s algorithmic, %d launches" % (ms_per_step, value, launches))
+    log("device-resident: %.1f ms per step (%.3f ms per degree step), %.0f GB/s algorithmic, %d launches" % (
+        ms_per_step, ms_per_step / D, value, launches))
 
     # ---- e2e: host vectors through the C ABI
     zh = torch.empty(n, dtype=torch.float64).uniform_(-1, 1).pin_memory(); yh = torch.empty(n, dtype=torch.float64).pin_memory()
 
     def step_host():
-        _lib.check(L.nm_pevsl_filter_host(P.h, pol.h, C.c_void_p(zh.data_ptr()), C.c_void_p(yh.data_ptr())))
+        _lib.check(L.nm_pevsl_filter_steps_host(P.h, pol.h, int(D), C.c_void_p(zh.data_ptr()), C.c_void_p(yh.data_ptr())))
     step_host()
     barrier()
     e2e_steps = max(1, min(a.steps, a.e2e_steps))
@@ -294,15 +405,12 @@ def main():
         step_host()
     e1.record(stream)
     barrier()
-    ms_e2e = max(e0.elapsed_time(e1), 0.0)
-    if use_dist:
-        import torch.distributed as dist
-        t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_e2e = float(t.item())
+    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
     e2e = dict(value=nbytes / (ms_e2e / e2e_steps * 1e-3) / 1e9, unit="GB/s", h2d_bytes_per_step=8 * n, d2h_bytes_per_step=8 * n,
                ms_per_step=ms_e2e / e2e_steps, steps=e2e_steps)
-    log("e2e (host vectors through the C ABI): %.1f ms per application" % (ms_e2e / e2e_steps))
+    log("e2e (host vectors through the C ABI): %.1f ms per step" % (ms_e2e / e2e_steps))
 
-    # ---- roofline of the dominant kernel: the fused ChebIter step on B~ (degB launches per B-solve)
+    # ---- per-kernel times of one degree step (live, CUDA events, back to back) and the bytes each must stream
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -310,34 +418,78 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    for _ in range(3):
-        _lib.check(L.nm_chebiter_solve_dev(mv.chebB, C.c_void_p(z.data_ptr()), C.c_void_p(y.data_ptr())))
-    torch.cuda.synchronize()
-    reps = 20
-    e0.record(stream)
-    for _ in range(reps):
-        _lib.check(L.nm_chebiter_solve_dev(mv.chebB, C.c_void_p(z.data_ptr()), C.c_void_p(y.data_ptr())))
-    e1.record(stream)
-    torch.cuda.synchronize()
-    us_launch = e0.elapsed_time(e1) * 1e3 / (reps * mv.degB)
+
+    def timeit(fn, reps):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return max_over_ranks(e0.elapsed_time(e1)) * 1e3 / reps
+
+    def pack_info(cheb):
+        kind = C.c_int(); pbytes = C.c_longlong()
+        _lib.check(L.nm_chebiter_pack_info(cheb, C.byref(kind), C.byref(pbytes)))
+        return kind.value, pbytes.value
+    knames = ("k_spmv_kron3<EpiCheb>", "k_pack<KRON3,EpiCheb>", "k_sell<KRON3,EpiCheb>", "k_slab<3,256,EpiCheb>",
+              "k_slabws<3,8,EpiCheb>", "k_slabpers<3,8>")
+    us_solveB = timeit(lambda: _lib.check(L.nm_chebiter_solve_dev(mv.chebB, C.c_void_p(z.data_ptr()), C.c_void_p(y.data_ptr()))), 10)
+    us_launch = us_solveB / mv.degB
     infoB = mvmod.parcsr_info(mv.sBV)
-    kind = C.c_int(); pbytes = C.c_longlong()
-    _lib.check(L.nm_chebiter_pack_info(mv.chebB, C.byref(kind), C.byref(pbytes)))
-    kname = ("k_spmv_kron3<EpiCheb>", "k_pack<KRON3,EpiCheb>", "k_sell<KRON3,EpiCheb>", "k_slab<3,256,EpiCheb>", "k_slabws<3,8,EpiCheb>")[kind.value]
-    bytes_launch = cheb_step_bytes(infoB["nnz"], infoB["nrow"])
-    fmt_bytes_launch = pbytes.value + 48 * infoB["nrow"]
-    achieved = bytes_launch / (us_launch * 1e-6) / 1e9
-    traffic = None                      # dram bytes per launch of this kernel from the committed ncu --set full capture
+    kindB, pbytesB = pack_info(mv.chebB)
+    algo_launch = cheb_step_bytes(infoB["nnz"], infoB["nrow"])
+    fmt_launch = pbytesB + 48 * infoB["nrow"]              # slab + r, d, x read and written once each
+    parts = {"B~ ChebIter step": dict(us=us_launch, per_degree=mv.degB, format_bytes=fmt_launch, algorithmic_bytes=algo_launch)}
+    if fem.fluidcase:
+        npz = mv.Ap.siz(rk)
+        zp = torch.empty(max(npz, 1), dtype=torch.float64, device="cuda").uniform_(-1, 1)
+        yp = torch.empty_like(zp)
+        us = timeit(lambda: _lib.check(L.nm_chebiter_solve_dev(mv.chebAp, C.c_void_p(zp.data_ptr()), C.c_void_p(yp.data_ptr()))), 10) / degAp
+        iAp = mvmod.parcsr_info(mv.sApV); _, pbAp = pack_info(mv.chebAp)
+        parts["Ap~ ChebIter step"] = dict(us=us, per_degree=degAp, format_bytes=pbAp + 48 * iAp["nrow"],
+                                          algorithmic_bytes=cheb_step_bytes(iAp["nnz"], iAp["nrow"]))
+        us_op = timeit(lambda: _lib.check(L.nm_op_apply_dev(mv.opA, C.c_void_p(z.data_ptr()), C.c_void_p(y.data_ptr()))), 5)
+        iA = mvmod.parcsr_info(mv.sAdV); iE = mvmod.parcsr_info(mv.sEV); iET = mvmod.parcsr_info(mv.sETV)
+        rest_fmt = (iA["fmt_bytes"] + 56 * iA["nrow"]) + (iE["fmt_bytes"] + 8 * iE["nrow"] + 8 * iE["ncol"]) + \
+                   (iET["fmt_bytes"] + 8 * iET["nrow"] + 8 * iET["ncol"])
+        rest_algo = filter_step_bytes(iA["nnz"], iA["nrow"]) + spmv_bytes(iE["nnz"], iE["nrow"], iE["ncol"]) + \
+            spmv_bytes(iET["nnz"], iET["nrow"], iET["ncol"])
+        parts["Ad + ET + E products"] = dict(us=max(us_op - us * degAp, 0.0), per_degree=1, format_bytes=rest_fmt,
+                                             algorithmic_bytes=rest_algo)
+    else:
+        us_op = timeit(lambda: _lib.check(L.nm_op_apply_dev(mv.opA, C.c_void_p(z.data_ptr()), C.c_void_p(y.data_ptr()))), 10)
+        iA = mvmod.parcsr_info(mv.sAV)
+        parts["A product"] = dict(us=us_op, per_degree=1, format_bytes=iA["fmt_bytes"] + 56 * iA["nrow"],
+                                  algorithmic_bytes=filter_step_bytes(iA["nnz"], iA["nrow"]))
+    for v in parts.values():
+        v["format_gbs"] = v["format_bytes"] / v["us"] / 1e3 if v["us"] > 0 else None
+        v["frac_of_hbm"] = v["format_gbs"] / peak if v["us"] > 0 else None
+    fmt_degree = sum(v["format_bytes"] * v["per_degree"] for v in parts.values())     # this rank's bytes per degree step
+    us_degree = ms_per_step * 1e3 / D
+    application = dict(us_per_degree_step=us_degree, format_bytes_per_degree_step_per_gpu=fmt_degree,
+                       format_gbs_per_gpu=fmt_degree / us_degree / 1e3, frac_of_hbm_per_gpu=fmt_degree / us_degree / 1e3 / peak,
+                       algorithmic_gbs=value, kernels=parts,
+                       note="format bytes = what each kernel must stream in ITS storage format (slab / ROW3 / CSR bytes + every "
+                            "vector it reads or writes once), no cache credit; value and e2e count the reference's CSR bytes")
+    traffic = None                      # dram bytes per step of this kernel from the committed ncu --set full capture
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if kind.value == tj.get("kind") and nr == 1 and tj.get("n_rows") == infoB["nrow"]:
+        if kindB == tj.get("kind") and tj.get("n_rows") == infoB["nrow"]:
             traffic = tj["traffic_bytes_per_launch"]
     except Exception:
         pass
-    roofline = dict(bound="hbm", kernel="%s (fused ChebIter step on B~, %s; us_per_launch includes the 2 permute kernels of a solve spread over degB launches)" % (kname, infoB["format"]),
+    achieved = fmt_launch / (us_launch * 1e-6) / 1e9
+    roofline = dict(bound="hbm", kernel="%s (fused ChebIter step on B~, %s; one launch = %d steps; us_per_launch is per STEP and "
+                                        "includes the 2 permute kernels of a solve)" % (knames[kindB], infoB["format"], mv.degB if kindB == 5 else 1),
                     achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, peak_source=peak_src,
-                    us_per_launch=us_launch, algorithmic_bytes_per_launch=bytes_launch,
-                    format_bytes_per_launch=fmt_bytes_launch, format_gbs=fmt_bytes_launch / (us_launch * 1e-6) / 1e9)
+                    us_per_launch=us_launch, bytes_per_launch=fmt_launch,
+                    bytes_note="bytes the kernel streams per step in its own format (slab + 6 vector passes); the CSR-equivalent "
+                               "(SURVEY 8d) figure is algorithmic_*",
+                    algorithmic_bytes_per_launch=algo_launch, algorithmic_gbs=algo_launch / (us_launch * 1e-6) / 1e9)
+    assert roofline["frac"] <= 1.05, "roofline fraction above 1: byte accounting is wrong"
     comm = None
     if use_dist:
         mode = C.c_int(); ng = C.c_int(); ns = C.c_int()
@@ -350,14 +502,20 @@ def main():
             _lib.check(L.nm_parcsr_halo_exchange_dev(mv.sBV, C.c_void_p(z.data_ptr())))
         e1.record(stream)
         barrier()
-        comm = dict(halo=("none", "nccl send/recv", "nvlink peer window (direct stores + flags)")[mode.value],
-                    us_per_exchange=e0.elapsed_time(e1) * 1e3 / 200, ghosts_rank0=ng.value, sends_rank0=ns.value,
-                    exchanges_per_filter_degree=mv.degB + (degAp + 3 if fem.fluidcase else 1))
-        log("halo exchange alone: %.1f us (%s), %d ghosts on rank 0" % (comm["us_per_exchange"], comm["halo"], ng.value))
+        comm = dict(halo_products=("none", "nccl send/recv", "nvlink peer window (direct stores + flags)")[mode.value],
+                    halo_chebiter="in-kernel: boundary rows stored into the peers' flag-in-data slots from the step's epilogue"
+                    if kindB == 5 else "per step", us_per_standalone_exchange=e0.elapsed_time(e1) * 1e3 / 200,
+                    ghosts_rank0=ng.value, sends_rank0=ns.value, standalone_exchanges_per_degree_step=3 if fem.fluidcase else 1,
+                    us_per_chebiter_step_B=us_launch)
+        log("halo exchange alone: %.1f us (%s), %d ghosts on rank 0" % (comm["us_per_standalone_exchange"], comm["halo_products"], ng.value))
     out = dict(metric="filtered_spmv_hbm_gbs", value=value, unit="GB/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
                ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
-               data="synthetic", config=config, clocks=cs.summary(), e2e=e2e, gpu_launches=launches, roofline=roofline,
-               setup_s=dict(assembly=t_asm, setupmatvec=t_setup, bounds=t_bounds))
+               data="synthetic", config=config, detail=detail, clocks=cs.summary(), e2e=e2e, gpu_launches=launches,
+               roofline=roofline, application=application, check=check,
+               value_note="CSR-equivalent (algorithmic) bytes of SURVEY 8d / time: the unit the CPU arm is measured in; it exceeds "
+                          "the HBM bandwidth because B = M (x) I3 is stored in 0.3 of its CSR bytes -- roofline / application "
+                          "carry the format-byte figures",
+               setup_s=dict(total=time.time() - t_start, assembly=t_asm, setupmatvec=t_setup, bounds=t_bounds))
     if comm:
         out["comm"] = comm
     if a.solve:
@@ -368,7 +526,8 @@ def main():
                             t_filter=r.t_filter, t_reorth=r.t_reorth, t_ritz=r.t_ritz,
                             max_res_over_lam=float((r.res2 / np.abs(r.eigval)).max()) if r.nev else None)
     if rank == 0 and nr == 1 and not a.no_cpu:
-        cops = cpu_ops_from(CGM, mv, bool(fem.fluidcase))
+        if cops is None:
+            cops = gather_cpu_ops(CGM, mv, bool(fem.fluidcase), 0, 1)
         cb, tm, kmax = time_cpu_sample(cops, pol, sz, mv.degB, degAp, a.cpu_seconds)
         out["cpu_baseline"] = cb
     if rank == 0:

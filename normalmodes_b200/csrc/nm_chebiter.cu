@@ -62,17 +62,32 @@ static void cheb_build_ppack(NmChebIter& C) {
     M.halo.send_idx.download(sidx.data(), sidx.size());
     // fused multi-GPU step (opt-in): every sent row must sit in a chunk that polls the arrival flags before it is
     // walked, i.e. the row itself must reference a ghost column (true for the symmetric B~ / Ap~)
-    bool fused = nm_env_int("NM_HALO_FUSED", 0) != 0 && C.pslab.nchunk > 0 && C.pslab.ws && M.halo.p2p;
-    if (fused)
-      for (int v : sidx) {
-        const int row = v / R;
-        bool ghost = false;
-        for (int p = rp[row]; p < rp[row + 1] && !ghost; ++p) ghost = idx[p] >= n;
-        if (!ghost) { fused = false; break; }
-      }
+    // in-kernel halo (boundary rows stored to the peers from the step's epilogue): the per-step fused kernel
+    // (NM_HALO_FUSED=1) and the persistent kernel.  Both need what a symmetric pattern gives: a row that gathers a
+    // ghost column owned by rank r is itself sent to r (its chunk then produces what r waits for before r can run
+    // ahead and overwrite the slots the chunk still reads), and every sent row gathers a ghost column.
+    bool sym = C.pslab.nchunk > 0 && C.pslab.ws && M.halo.p2p;
+    if (sym) {
+      const int P = nm_ctx().nranks;
+      std::vector<unsigned char> sent((size_t)n, 0), needs((size_t)n, 0);       // bit r: sent to / gathers from rank r
+      for (int r = 0; r < P; ++r)
+        for (int i = M.halo.send_off[r]; i < M.halo.send_off[r + 1]; ++i) sent[sidx[i] / R] |= (unsigned char)(1u << r);
+      const int ncolb = M.ncol / R;
+      for (int row = 0; row < n; ++row)
+        for (int p = rp[row]; p < rp[row + 1]; ++p)
+          if (idx[p] >= ncolb) {
+            const int g = (idx[p] - ncolb) * R;                                  // position in the ghost tail
+            int r = 0;
+            while (r + 1 < P && g >= M.halo.recv_off[r + 1]) ++r;
+            needs[row] |= (unsigned char)(1u << r);
+          }
+      for (int row = 0; row < n && sym; ++row) sym = sent[row] == needs[row];
+    }
+    const bool fused = sym && nm_env_int("NM_HALO_FUSED", 0) != 0;
+    C.pers_multi_ok = sym;
     for (int& v : sidx) v = R * newid[v / R] + v % R;
     C.send_idx_p.from_host(sidx);
-    if (fused) {
+    if (sym) {
       const int P = nm_ctx().nranks;
       std::vector<int> cnt(n + 1, 0);
       for (int v : sidx) cnt[v / R + 1]++;
@@ -89,9 +104,43 @@ static void cheb_build_ppack(NmChebIter& C) {
         }
       C.push_off.from_host(cnt);
       C.push_ent.alloc(std::max<size_t>(ent.size(), 1)); C.push_ent.upload(ent.data(), ent.size());
-      C.fused = true;
+      C.fused = fused;
     }
   }
+}
+
+// Persistent kernel (k_slabpers): stages per CTA from the shared memory left beside the co-resident CTAs of an SM,
+// Chebyshev coefficients and the grid-barrier counter on the device, flag-in-data ghost slots on several GPUs.
+static void cheb_setup_pers(NmChebIter& C) {
+  NmParcsr& M = *C.M;
+  NmCtx& c = nm_ctx();
+  NmSlab& S = C.pslab;
+  C.pers = false;
+  const bool want = nm_env_int("NM_SLAB_PERS", 1) != 0 && S.nchunk > 0 && S.ws && S.max_chunks_per_cta <= NM_SLAB_MAXDESC;
+  // collective part first: every rank takes the same branch (the halo plan exists on all ranks or on none)
+  bool multi_ok = true;
+  if (c.nranks > 1) {
+    double v = (want && (M.halo.nsend == 0 || C.pers_multi_ok) && (M.halo.nghost == 0) == (M.halo.nsend == 0)) ? 1.0 : 0.0;
+    if (!c.p2p) v = 0.0;
+    DBuf<double> d(1);
+    d.upload(&v, 1);
+    NM_NCCL(ncclAllReduce(d.p, d.p, 1, ncclDouble, ncclMin, c.nccl, c.stream));
+    d.download(&v, 1);
+    multi_ok = v > 0.5;
+    if (multi_ok) multi_ok = nm_halo_ll_setup(M.halo);
+  }
+  if (!want || !multi_ok) return;
+  const int per_sm = std::max(1, nm_div_up(S.grid, c.sm_count));
+  const int budget = std::min(227 * 1024, (228 * 1024) / per_sm - 1024);
+  const int fixed = (int)((NM_SLAB_MAXDESC * sizeof(NmPackDesc) + 256 + 8 * (size_t)S.nxs * S.xs_doubles + 15) & ~(size_t)15);
+  int nst = (budget - fixed) / std::max(S.stage_bytes, 16);
+  nst = std::max(0, std::min(8, std::min(nst, nm_env_int("NM_SLAB_PERS_STAGES", 8))));
+  if (nst < 2) return;
+  S.pers_nstage = nst; S.pers_smem = fixed + nst * S.stage_bytes;
+  C.ak_dev.from_host(C.ak); C.bk_dev.from_host(C.bk);
+  C.gbar.alloc(2); C.gbar.zero();
+  C.gbar_base = 0;
+  C.pers = true;
 }
 
 // One step of the fused multi-GPU iteration: kernel k polls the flags of the values it gathers (pushed by the peers'
@@ -152,6 +201,7 @@ NmChebIter* nm_chebiter_build(double lb, double ub, int deg, NmParcsr* M) {
   const size_t n = M->nrow > 0 ? M->nrow : 1;
   C->r.alloc(n); C->d0.alloc(n); C->d1.alloc(n);
   cheb_build_ppack(*C);
+  cheb_setup_pers(*C);
   return C.release();
 }
 
@@ -173,6 +223,51 @@ void nm_chebiter_solve(NmChebIter& C, const double* b, double* x) {
     c.launches++;
     b = C.bp.p;
     x = C.xp.p;
+  }
+  if (C.pers) {
+    // the whole iteration in ONE cooperative launch (k_slabpers); several GPUs: the boundary values of b go into the
+    // peers' flag-in-data slots first (what step 0 gathers), everything else is exchanged inside the kernel
+    NmSlabPersArgs W;
+    memset(&W, 0, sizeof(W));
+    NmSlab& S = C.pslab;
+    W.a.blob = S.blob.p; W.a.desc = S.desc.p; W.a.cta_first = S.cta_first.p; W.a.ncol = M.ncol;
+    W.a.stage_bytes = S.stage_bytes; W.a.xs_doubles = S.xs_doubles; W.a.nstage = S.pers_nstage;
+    W.nxs = S.nxs; W.np = S.nprod; W.deg = C.deg;
+    W.b = b; W.r = C.r.p; W.d0 = C.d0.p; W.d1 = C.d1.p; W.xout = x;
+    W.ak = C.ak_dev.p; W.bk = C.bk_dev.p; W.inv_theta = 1.0 / C.theta;
+    W.gbar = C.gbar.p; W.gbase = C.gbar_base;
+    NmHalo& h = M.halo;
+    if (c.nranks > 1 && h.nsend > 0) {
+      const unsigned long long e0 = ++h.epoch;
+      W.tag0 = (unsigned)e0;
+      nm_halo_push_ll(M, b, C.send_idx_p.p, W.tag0, (int)(W.tag0 % 3u));
+      for (int q = 0; q < 3; ++q) {
+        W.ll_in[q] = (const unsigned long long*)(c.win + h.win_ll[q]);
+        for (int r = 0; r < c.nranks; ++r)
+          if (r != c.rank && h.send_cnt[r] > 0) W.ll_out[q][r] = (unsigned long long*)(c.peer_win[r] + h.peer_ll[q][r]);
+      }
+      W.push_off = C.push_off.p; W.push_ent = C.push_ent.p; W.hstatus = c.dev_status;
+      h.epoch = e0 + (unsigned long long)(C.deg - 1);
+    }
+    bool launched = true;
+    try {
+      nm_slabpers_dispatch(M, S, W);
+    } catch (const NmError&) {
+      // not co-resident on this device (cooperative launch refused): per-step launches from now on.  Only legal on one
+      // rank, where nothing has been exchanged yet; ranks must not diverge.
+      cudaGetLastError();
+      NM_REQUIRE(c.nranks == 1, "persistent ChebIter kernel could not be launched on rank %d", c.rank);
+      C.pers = false;
+      launched = false;
+    }
+    if (launched) {
+      C.gbar_base += (unsigned long long)(C.deg - 1) * (unsigned long long)S.grid;
+      k_perm_scatter<<<nm_div_up(M.nrow, 256), 256, 0, c.stream>>>(xout, C.xp.p, order_dev, nblk, R);
+      c.launches++;
+      C.nsolve++;
+      C.nmatvec += C.deg;
+      return;
+    }
   }
   const double* din = b;
   NmHaloWait fused_poll;
@@ -231,11 +326,12 @@ extern "C" int nm_chebiter_solve_dev(void* h, const double* b_dev, double* x_dev
   NM_API_END
 }
 // kind: 0 = plain kernels on the caller's numbering, 1 = TMA-staged packed kernel (k_pack), 2 = sliced JDS (k_sell),
-// 3 = TMA-staged warp-sliced ELL slabs (k_slab), 4 = the same, warp-specialised (k_slabws); all on vectors kept in pack order; bytes = matrix bytes one iteration step streams
+// 3 = TMA-staged warp-sliced ELL slabs (k_slab), 4 = the same, warp-specialised (k_slabws), 5 = the whole iteration in one
+// persistent cooperative launch (k_slabpers, default); all on vectors kept in pack order; bytes = matrix bytes one iteration step streams
 extern "C" int nm_chebiter_pack_info(void* h, int* kind, long long* bytes) {
   NM_API_BEGIN
   NmChebIter& C = *(NmChebIter*)h;
-  const int k = C.pslab.nchunk > 0 ? (C.pslab.ws ? 4 : 3) : (C.psell.nchunk > 0 ? 2 : (C.ppack.nchunk > 0 ? 1 : 0));
+  const int k = C.pslab.nchunk > 0 ? (C.pers ? 5 : (C.pslab.ws ? 4 : 3)) : (C.psell.nchunk > 0 ? 2 : (C.ppack.nchunk > 0 ? 1 : 0));
   if (kind) *kind = k;
   if (bytes) *bytes = k >= 3 ? C.pslab.bytes : (k == 2 ? C.psell.bytes : (k == 1 ? C.ppack.bytes : C.M->fmt_bytes));
   NM_API_END

@@ -133,6 +133,11 @@ struct NmHalo {
   std::vector<int> cnt_all;                             // P x P: cnt_all[r*P+s] = ghosts rank r receives from rank s
   unsigned long long epoch = 0;                         // exchanges done (flag value of the next one = epoch + 1)
   bool p2p = false;
+  // flag-in-data ("LL") ghost slots of the persistent ChebIter kernel (k_slabpers): 16 bytes per ghost value =
+  // {lo32, tag, hi32, tag}, three rotating buffers in the window; no fences, flags or atomics on the exchange path
+  bool ll = false;
+  size_t win_ll[3] = {0, 0, 0};
+  std::vector<size_t> peer_ll[3];
 };
 
 // Packed row-block format of the streaming SpMV (nm_spmv.cuh / nm_pack.cu).  The (block-)rows are ordered for
@@ -184,6 +189,8 @@ struct NmSell {
 // element first(c)+j).
 struct NmSlabHeader { int nr, nd, nslice, first, nep, gmax, has_ghost, pad2; };   // 32 bytes; gmax: most lanes per row
 struct NmSlab {
+  // persistent kernel (k_slabpers): stages per CTA when the whole iteration runs in one cooperative launch
+  int pers_nstage = 0, pers_smem = 0;
   DBuf<unsigned char> blob;
   DBuf<NmPackDesc> desc;
   DBuf<int> cta_first;                    // grid+1: first chunk of each CTA (balanced by bytes)
@@ -240,10 +247,16 @@ struct NmChebIter {
   long long ppack_version = -1;
   DBuf<double> bp, xp;                    // b and x in pack order
   DBuf<int> send_idx_p;                   // halo send list in pack order
-  // NM_HALO_FUSED=1 (off by default): per pack-order index row the peer stores of its new direction
+  // per pack-order index row the peer stores of its new direction: in-kernel halo of the persistent kernel
+  // (k_slabpers, default) and of the per-step fused kernel (NM_HALO_FUSED=1)
   bool fused = false;
+  bool pers = false;                      // whole iteration in ONE cooperative launch (grid barrier between steps)
+  bool pers_multi_ok = false;             // the halo pattern allows the in-kernel exchange (symmetric)
   DBuf<int> push_off;
   DBuf<NmPushEnt> push_ent;
+  DBuf<double> ak_dev, bk_dev;
+  DBuf<unsigned long long> gbar;          // grid-barrier counter of the persistent kernel (monotonic)
+  unsigned long long gbar_base = 0;
   long long nsolve = 0, nmatvec = 0;
   double t_total = 0;
 };
@@ -305,6 +318,8 @@ void nm_halo_exchange(NmParcsr& M, const double* x, const int* send_idx = nullpt
 // has no halo (then nothing was done and the caller uses nm_halo_exchange).
 struct NmHaloWait { const unsigned long long* flags; unsigned mask; unsigned long long epoch; int* status; };
 bool nm_halo_push_nowait(NmParcsr& M, const double* x, const int* send_idx, NmHaloWait* w);
+bool nm_halo_ll_setup(NmHalo& h);            // collective: LL ghost slots in the peer window; false without a window
+void nm_halo_push_ll(NmParcsr& M, const double* x, const int* send_idx, unsigned tag, int buf);
 void nm_spmv(NmParcsr& M, const double* x, double* y);                 // y = M x   (device pointers)
 void nm_spmv_add(NmParcsr& M, const double* x, double* y);             // y += M x
 // packed format (nm_pack.cu): rp/idx = host row pointers and column ids of the chosen format, n (block-)rows

@@ -141,6 +141,57 @@ void nm_halo_exchange(NmParcsr& M, const double* x, const int* send_idx) {
   h.xg_cur = h.xg.p;
 }
 
+// ---- flag-in-data exchange of the persistent ChebIter kernel: slots + the push of the right-hand side (step 0's gather)
+struct NmPushLLArgs {
+  int nsend;
+  int send_off[9];
+  unsigned long long* peer_ll[8];           // this rank's block of slots in each peer's buffer
+  unsigned tag;
+};
+__global__ void k_halo_push_ll(NmPushLLArgs A, const double* __restrict__ x, const int* __restrict__ idx) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.nsend; i += gridDim.x * blockDim.x) {
+    int r = 0;
+    while (i >= A.send_off[r + 1]) ++r;
+    nm_ll_store(A.peer_ll[r] + 2 * (size_t)(i - A.send_off[r]), x[idx[i]], A.tag);
+  }
+}
+void nm_halo_push_ll(NmParcsr& M, const double* x, const int* send_idx, unsigned tag, int buf) {
+  NmCtx& c = nm_ctx();
+  NmHalo& h = M.halo;
+  if (h.nsend == 0) return;
+  NM_REQUIRE(h.ll, "nm_halo_push_ll without LL slots");
+  NmPushLLArgs A;
+  A.nsend = h.nsend; A.tag = tag;
+  for (int r = 0; r < 8; ++r) A.peer_ll[r] = nullptr;
+  for (int r = 0; r <= 8; ++r) A.send_off[r] = h.send_off[std::min(r, c.nranks)];
+  for (int r = 0; r < c.nranks; ++r)
+    if (r != c.rank && h.send_cnt[r] > 0)
+      A.peer_ll[r] = (unsigned long long*)(c.peer_win[r] + h.peer_ll[buf][r]) + 2 * (size_t)h.peer_base[r];
+  const int blocks = std::max(1, std::min(32, nm_div_up(h.nsend, 1024)));
+  k_halo_push_ll<<<blocks, 256, 0, c.stream>>>(A, x, send_idx ? send_idx : (const int*)h.send_idx.p);
+  c.launches++;
+}
+bool nm_halo_ll_setup(NmHalo& h) {
+  NmCtx& c = nm_ctx();
+  if (h.ll) return true;
+  if (!c.p2p || !h.p2p) return false;
+  const int P = c.nranks;
+  NM_REQUIRE(P <= 8, "peer-window halo: at most 8 ranks (one NVSwitch box)");
+  long long mine[3];
+  for (int b = 0; b < 3; ++b) { h.win_ll[b] = nm_win_alloc(16 * (size_t)std::max(h.nghost, 1)); mine[b] = (long long)h.win_ll[b]; }
+  DBuf<long long> d_mine(3), d_all((size_t)3 * P);
+  d_mine.upload(mine, 3);
+  NM_NCCL(ncclAllGather(d_mine.p, d_all.p, 3, ncclInt64, c.nccl, c.stream));
+  std::vector<long long> all((size_t)3 * P);
+  d_all.download(all.data(), all.size());
+  for (int b = 0; b < 3; ++b) {
+    h.peer_ll[b].assign(P, 0);
+    for (int r = 0; r < P; ++r) h.peer_ll[b][r] = (size_t)all[3 * r + b];
+  }
+  h.ll = true;
+  return true;
+}
+
 // Window slots of one matrix' halo (collective: every rank calls this for the same matrices in the same order).
 // cnt: P x P matrix, cnt[r*P + s] = ghosts rank r receives from rank s.
 static void halo_p2p_setup(NmHalo& h, const std::vector<int>& cnt) {

@@ -544,7 +544,7 @@ extern "C" int nm_slab_host_selftest(int n, int ncolb, int R, const int* rp_, co
   std::vector<double> xs;
   long long model_wavefronts = 0, model_ideal = 0;
   for (int g = 0; g < H.grid; ++g) {
-    NM_REQUIRE(H.cta_first[g + 1] - H.cta_first[g] >= 1 && H.cta_first[g + 1] - H.cta_first[g] <= std::min(NM_SLAB_MAXDESC, H.threads),
+    NM_REQUIRE(H.cta_first[g + 1] - H.cta_first[g] >= 1 && H.cta_first[g + 1] - H.cta_first[g] <= NM_SLAB_MAXDESC,
                "slab: CTA %d has %d chunks", g, H.cta_first[g + 1] - H.cta_first[g]);
     for (int ci = H.cta_first[g]; ci < H.cta_first[g + 1]; ++ci) {
       const unsigned char* st = H.blob.data() + 16ull * H.desc[ci].off16;

@@ -21,7 +21,7 @@
 #pragma once
 #include "nm_spmv.cuh"
 
-#define NM_SLAB_MAXDESC 64             // chunk descriptors a CTA keeps in shared memory
+#define NM_SLAB_MAXDESC 256            // chunk descriptors a CTA keeps in shared memory
 
 struct NmSlabArgs {
   const unsigned char* blob;
@@ -200,7 +200,7 @@ __device__ __forceinline__ void nm_mbar_wait_bounded(uint64_t* b, uint32_t parit
         : "=r"(done)
         : "r"(a), "r"(parity)
         : "memory");
-    if (!done && clock64() - t0 > 4000000000ll) __trap();       // ~2 s: a lost arrival must not hang the GPU
+    if (!done && clock64() - t0 > 40000000000ll) __trap();      // ~20 s (above the 10 s peer waits): a lost arrival must not hang the GPU
   } while (!done);
 }
 __device__ __forceinline__ void nm_mbar_arrive(uint64_t* b) {
@@ -433,6 +433,287 @@ __global__ void __launch_bounds__(32 * (NC + 8)) k_slabws(NmSlabWsArgs W, Epi ep
       }
     }
   }
+}
+
+// ---------------------------------------------------------------- persistent variant: the WHOLE iteration in one launch
+// "one persistent kernel per solve".  The per-step launches of k_slabws cost ~5 us of drain + launch +
+// first-gather latency per step even with dependent launch (an Ap~ step on the bench workload is 9 us whatever the
+// tile shape, profiles/r1d_sweep_slab.json), and on several GPUs every step adds two system-scope fences and a flag
+// flight.  k_slabpers is launched cooperatively ONCE per solve: every CTA keeps its chunk range for all deg steps;
+//   * matrix: the first P chunks of a CTA stay pinned in their stages (all of them when the range fits the ring: the
+//     slab is then read from HBM once per SOLVE); the others stream through 2 ring stages, the copies of step k+1
+//     running ahead across the step boundary (the matrix is read-only);
+//   * vectors: a row's r, x, d are read and written by the same thread in every step (same-thread RAW through
+//     global memory); only the GATHERED direction crosses CTAs -> one grid barrier per step, waited for by the
+//     producer warps only (arrive: one fence + atomic per CTA after its consumers' named barrier; wait: one polling
+//     thread, then a gpu-scope fence -- which also drops the stale L1 lines of the alternating d buffers -- and the
+//     producers' named barrier).  Consumer warps never wait for the grid: they block on full_xs as before;
+//   * halo (several GPUs): boundary rows go straight from the epilogue into the peers' flag-in-data slots
+//     (nm_ll_store, three rotating buffers, tag = step epoch); the producers poll the slots they gather
+//     (nm_ll_load).  No fence, flag or atomic between GPUs; chunks with ghost columns come last in every CTA's range
+//     and their rows are sent a whole step before they are needed.  Why three buffers are enough: the local grid
+//     barrier keeps a GPU's CTAs within one step of each other, and a peer's step k+2 needs ALL of our step k+1.
+struct NmSlabPersArgs {
+  NmSlabArgs a;             // blob, desc, cta_first, ncol, stage_bytes, xs_doubles, nstage (x, xg unused)
+  int nxs, np, deg;
+  const double* b;          // right-hand side, pack order
+  double* r; double* d0; double* d1; double* xout;
+  const double* ak; const double* bk;
+  double inv_theta;
+  unsigned long long* gbar; // grid-barrier counter (monotonic over the solves of this ChebIter)
+  unsigned long long gbase; // its value when this launch starts
+  // several GPUs (null / 0 on one)
+  const unsigned long long* ll_in[3];   // this rank's ghost slots, by tag % 3
+  unsigned long long* ll_out[3][8];     // this rank's block of slots in each peer's buffers
+  const int* push_off; const NmPushEnt* push_ent;
+  unsigned tag0;            // tag of the values step 0 gathers (pushed by nm_halo_push_ll)
+  int* hstatus;
+};
+
+template <int R>
+__device__ __forceinline__ void nm_slab_gather_ll(const NmSlabView& v, double* xs, const double* __restrict__ x,
+                                                  const unsigned long long* ll, unsigned tag, int* status, int ncol,
+                                                  int t, int nthreads) {
+  const int tot = R * v.h.nd;
+  for (int j = t; j < tot; j += nthreads) {
+    const int node = (R == 1) ? j : j / 3;
+    const int c = R * v.scols[node] + (j - R * node);
+    if (c < ncol) { nm_cp_async8(xs + j, x + c); continue; }
+    double val = 0.0;
+    const unsigned long long* slot = ll + 2 * (size_t)(c - ncol);
+    const long long t0 = clock64();
+    while (!nm_ll_load(slot, tag, &val)) {
+      if (*(volatile int*)status != 0) break;                                    // an earlier wait already failed
+      if (clock64() - t0 > 20000000000ll) { atomicOr(status, 1); break; }        // ~10 s: peer stalled or died
+    }
+    xs[j] = val;
+  }
+  __threadfence_block();                                         // the plain stores above precede the barrier arrival
+}
+
+template <int R, int NC>
+__global__ void __launch_bounds__(32 * (NC + 8)) k_slabpers(NmSlabPersArgs W) {
+  const NmSlabArgs& A = W.a;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c0 = A.cta_first[blockIdx.x];
+  const int n = A.cta_first[blockIdx.x + 1] - c0;                // >= 1 for every CTA (packer)
+  const int S = A.nstage, X = W.nxs, NP = W.np, deg = W.deg;
+  NmPackDesc* sdesc = (NmPackDesc*)smem;
+  uint64_t* full_blob = (uint64_t*)(smem + NM_SLAB_MAXDESC * sizeof(NmPackDesc));
+  uint64_t* empty_blob = full_blob + 8;
+  uint64_t* full_xs = full_blob + 16;
+  uint64_t* empty_xs = full_blob + 24;
+  double* xs0 = (double*)(full_blob + 32);
+  unsigned char* stage0 =
+      smem + ((NM_SLAB_MAXDESC * sizeof(NmPackDesc) + 256 + 8 * (size_t)X * A.xs_doubles + 15) & ~(size_t)15);
+  for (int i = tid; i < n; i += blockDim.x) sdesc[i] = A.desc[c0 + i];
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { nm_mbar_init(full_blob + s, 1); nm_mbar_init(empty_blob + s, NC); }
+    for (int x = 0; x < X; ++x) { nm_mbar_init(full_xs + x, 32 * NP); nm_mbar_init(empty_xs + x, NC); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // pinned chunks [0, P) sit in stages [0, P); the others cycle through the RG ring stages behind them in the order
+  // q = k (n - P) + (it - P) over the whole solve
+  const int P = n <= S ? n : S - 2, RG = n <= S ? 0 : 2, NR = n - P;
+  const bool multi = W.push_off != nullptr;
+  if (warp >= NC) {
+    // ================================================= producers
+    const int pw = warp - NC;
+    const int ptid = pw * 32 + lane, pthreads = 32 * NP;
+    uint64_t policy = 0;
+    const long long Q = (long long)deg * NR;                     // ring copies of the whole solve
+    long long issued = 0;
+    auto issue = [&](int chunk, int s) {
+      const NmPackDesc d = sdesc[chunk];
+      nm_mbar_expect_tx(full_blob + s, d.bytes);
+      nm_bulk_g2s(stage0 + (size_t)s * A.stage_bytes, A.blob + 16ull * d.off16, d.bytes, full_blob + s, policy);
+    };
+    // ring copy `issued` goes into stage P + issued % RG once copy issued - RG has been released by the consumers;
+    // need >= 0: block until copy `need` is on its way, otherwise only take what is free
+    auto pump = [&](long long need) {
+      while (issued < Q) {
+        const long long rel = issued - RG;
+        if (rel >= 0) {
+          uint64_t* eb = empty_blob + P + (int)(rel % RG);
+          const uint32_t par = (uint32_t)((rel / RG) & 1);
+          if (issued <= need) nm_mbar_wait_bounded(eb, par);
+          else {
+            uint32_t done;
+            asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(nm_smem_u32(eb)), "r"(par) : "memory");
+            if (!done) break;
+          }
+        }
+        issue(P + (int)(issued % NR), P + (int)(issued % RG));
+        ++issued;
+      }
+    };
+    if (ptid == 0) {
+      policy = nm_policy_evict_first();
+      for (int j = 0; j < P; ++j) issue(j, j);
+      pump(-1);
+    }
+    const int ncol = A.ncol;
+    for (int k = 0; k < deg; ++k) {
+      const double* __restrict__ x = k == 0 ? W.b : ((k & 1) ? W.d0 : W.d1);      // direction written by step k-1
+      if (k > 0) {
+        // grid barrier: every CTA has stored (and fenced) its step k-1 directions
+        if (ptid == 0) {
+          const unsigned long long target = W.gbase + (unsigned long long)k * gridDim.x;
+          unsigned long long v;
+          const long long t0 = clock64();
+          for (;;) {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(W.gbar) : "memory");
+            if (v >= target) break;
+            if (clock64() - t0 > 60000000000ll) __trap();                         // ~30 s (above the peer and mbarrier limits): never hang the GPU
+          }
+          __threadfence();                                                       // also drops this SM's stale L1 lines of d
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(pthreads) : "memory");
+      }
+      const unsigned tag = W.tag0 + (unsigned)k;
+      const unsigned long long* ll = multi ? W.ll_in[tag % 3u] : nullptr;
+      for (int it = 0; it < n; ++it) {
+        const long long gx = (long long)k * n + it;
+        const int xb = (int)(gx % X);
+        int s; uint32_t par;
+        if (it < P) { s = it; par = 0; }
+        else {
+          const long long q = (long long)k * NR + (it - P);
+          s = P + (int)(q % RG); par = (uint32_t)((q / RG) & 1);
+          if (ptid == 0) pump(q);
+        }
+        nm_mbar_wait_bounded(full_blob + s, par);
+        if (gx >= X) nm_mbar_wait_bounded(empty_xs + xb, (uint32_t)(((gx / X) - 1) & 1));
+        const NmSlabView v = nm_slab_view(stage0 + (size_t)s * A.stage_bytes);
+        double* xs = xs0 + (size_t)xb * A.xs_doubles;
+        if (multi && v.h.has_ghost) nm_slab_gather_ll<R>(v, xs, x, ll, tag, W.hstatus, ncol, ptid, pthreads);
+        else nm_slab_gather<R>(v, xs, x, x, ncol, ptid, pthreads);
+        nm_cp_async_mbar_arrive_noinc(full_xs + xb);
+        if (ptid == 0 && RG) pump(-1);
+        __syncwarp();
+      }
+    }
+    return;
+  }
+  // =================================================== consumers
+  const unsigned cthreads = 32 * NC;
+  for (int k = 0; k < deg; ++k) {
+    EpiCheb epi;
+    epi.first = (k == 0); epi.last = (k == deg - 1);
+    epi.r_in = epi.first ? W.b : W.r;
+    epi.d_in = k == 0 ? W.b : ((k & 1) ? W.d0 : W.d1);
+    epi.r_out = W.r;
+    epi.d_out = (k & 1) ? W.d1 : W.d0;
+    epi.x = W.xout;
+    epi.inv_theta = W.inv_theta; epi.ak = W.ak[k]; epi.bk = W.bk[k];
+    const unsigned otag = W.tag0 + (unsigned)k + 1u;             // tag of this step's directions
+    const bool push = multi && !epi.last;
+    for (int it = 0; it < n; ++it) {
+      const long long gx = (long long)k * n + it;
+      const int xb = (int)(gx % X);
+      int s; uint32_t par;
+      if (it < P) { s = it; par = 0; }
+      else {
+        const long long q = (long long)k * NR + (it - P);
+        s = P + (int)(q % RG); par = (uint32_t)((q / RG) & 1);
+      }
+      nm_mbar_wait_bounded(full_blob + s, par);
+      const NmSlabView v = nm_slab_view(stage0 + (size_t)s * A.stage_bytes);
+      const double* xs = xs0 + (size_t)xb * A.xs_doubles;
+      const bool walk = warp < v.h.nslice;
+      const unsigned lw = walk ? (unsigned)v.slane[tid] : 0u;
+      const bool own = (lw & 0x8000u) != 0u;
+      const int prow = v.h.first + (int)(lw & 0x3ffu);
+      const int row0 = R * prow;
+      typename EpiCheb::In in[R];
+      if (own) {
+#pragma unroll
+        for (int c = 0; c < R; ++c) in[c] = epi.load(row0 + c);
+      }
+      double acc[R];
+#pragma unroll
+      for (int c = 0; c < R; ++c) acc[c] = 0.0;
+      uint2 t = make_uint2(0u, 0u);
+      if (walk) t = v.tbl[warp];
+      nm_mbar_wait_bounded(full_xs + xb, (uint32_t)((gx / X) & 1));
+      if (walk) {
+        const double* pv = v.sv + t.x + lane;
+        const unsigned short* pi = v.sidx + t.x + lane;
+        const int w = (int)t.y;
+#pragma unroll 4
+        for (int kk = 0; kk < w; ++kk) {
+          const double m = pv[32 * kk];
+          const double* xp = xs + R * (int)pi[32 * kk];
+#pragma unroll
+          for (int c = 0; c < R; ++c) acc[c] += m * xp[c];
+        }
+      }
+      const int gmax = v.h.gmax;
+      __syncwarp();
+      if (lane == 0) {
+        if (it >= P) nm_mbar_arrive(empty_blob + s);             // pinned stages are never refilled
+        nm_mbar_arrive(empty_xs + xb);
+      }
+      for (int q = 0; (1 << q) < gmax; ++q) {
+#pragma unroll
+        for (int c = 0; c < R; ++c) {
+          const double other = __shfl_down_sync(0xffffffffu, acc[c], 1 << q);
+          if (lw & (1u << (10 + q))) acc[c] += other;
+        }
+      }
+      if (own) {
+        double dn[R];
+#pragma unroll
+        for (int c = 0; c < R; ++c) dn[c] = epi.apply_dn(row0 + c, acc[c], in[c]);
+        if (push) {
+          for (int e = W.push_off[prow]; e < W.push_off[prow + 1]; ++e) {
+            const NmPushEnt pe = W.push_ent[e];
+            double val = dn[0];
+#pragma unroll
+            for (int c = 1; c < R; ++c) if (pe.comp == c) val = dn[c];
+            nm_ll_store(W.ll_out[otag % 3u][pe.peer] + 2 * (size_t)pe.dst, val, otag);
+          }
+        }
+      }
+    }
+    if (k < deg - 1) {
+      // this CTA's directions of step k are stored: count it in at the grid barrier (the producers wait)
+      asm volatile("bar.sync 2, %0;" ::"r"(cthreads) : "memory");
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(W.gbar, 1ull);
+      }
+    }
+  }
+}
+
+template <int R, int NC>
+static inline void nm_slabpers_launch_t(NmSlab& S, const NmSlabPersArgs& W) {
+  NmCtx& c = nm_ctx();
+  static bool attr_set = false;                                  // per template instantiation
+  if (!attr_set) {
+    NM_CUDA(cudaFuncSetAttribute(k_slabpers<R, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(S.grid); cfg.blockDim = dim3(32 * (NC + S.nprod)); cfg.dynamicSmemBytes = S.pers_smem; cfg.stream = c.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;                   // every CTA resident: the grid barrier cannot deadlock
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  NM_CUDA(cudaLaunchKernelEx(&cfg, k_slabpers<R, NC>, W));
+  c.launches++;
+}
+static inline void nm_slabpers_dispatch(NmParcsr& M, NmSlab& S, const NmSlabPersArgs& W) {
+  const bool blk = M.format == NM_FMT_KRON3;
+  if (S.threads == 512) { if (blk) nm_slabpers_launch_t<3, 16>(S, W); else nm_slabpers_launch_t<1, 16>(S, W); }
+  else if (S.threads == 256) { if (blk) nm_slabpers_launch_t<3, 8>(S, W); else nm_slabpers_launch_t<1, 8>(S, W); }
+  else if (S.threads == 64) { if (blk) nm_slabpers_launch_t<3, 2>(S, W); else nm_slabpers_launch_t<1, 2>(S, W); }
+  else { if (blk) nm_slabpers_launch_t<3, 4>(S, W); else nm_slabpers_launch_t<1, 4>(S, W); }
 }
 
 template <int R, int NC, bool FUSED, class Epi>

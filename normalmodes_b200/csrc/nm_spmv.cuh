@@ -162,6 +162,24 @@ struct EpiFilter {
   }
 };
 
+// ---------------------------------------------------------------- flag-in-data halo slots
+// One ghost value = 16 bytes {lo32, tag, hi32, tag} written with two 8-byte words in ONE vector store (each 8-byte
+// word lands atomically, the scheme of NCCL's LL protocol): the reader polls the slot itself until both tags match,
+// so the exchange needs no fence, no arrival flag and no atomic -- its latency is one NVLink store flight.
+__device__ __forceinline__ void nm_ll_store(unsigned long long* slot, double v, unsigned tag) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long w0 = (u & 0xffffffffull) | ((unsigned long long)tag << 32);
+  const unsigned long long w1 = (u >> 32) | ((unsigned long long)tag << 32);
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ bool nm_ll_load(const unsigned long long* slot, unsigned tag, double* v) {
+  unsigned a, fa, b, fb;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(slot) : "memory");
+  if (fa != tag || fb != tag) return false;
+  *v = __longlong_as_double((long long)(((unsigned long long)b << 32) | a));
+  return true;
+}
+
 // ================================================================ streaming kernel
 __device__ __forceinline__ uint32_t nm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void nm_mbar_init(uint64_t* b, int count) {

@@ -23,6 +23,8 @@ typedef struct {
 } csr_t;
 
 int nmcpu_threads(void) { return omp_get_max_threads(); }
+/* torchrun exports OMP_NUM_THREADS=1 to every rank: the caller sets the team size from its affinity mask instead */
+void nmcpu_set_threads(int n) { if (n >= 1) omp_set_num_threads(n); }
 
 /* y = A x */
 void nmcpu_spmv(int nrow, const int* ia, const int* ja, const double* a, const double* x, double* y) {

@@ -39,6 +39,14 @@ def lib():
     if _lib is None:
         build()
         _lib = C.CDLL(LIB)
+        # all the host cores this process may run on, whatever OMP_NUM_THREADS says: torchrun exports
+        # OMP_NUM_THREADS=1 to every rank, which would time the CPU arm on one core (NM_CPU_THREADS overrides)
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+        n = int(os.environ.get("NM_CPU_THREADS", n))
+        _lib.nmcpu_set_threads(int(n))
     return _lib
 
 

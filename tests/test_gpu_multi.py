@@ -27,15 +27,16 @@ def _ngpu():
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
 def test_two_ranks_halo_exchange_and_solve():
-    """Default transport: NVLink peer window, push without wait + arrival flags polled inside the ChebIter step kernel."""
+    """Default: persistent ChebIter kernel, boundary rows stored into the peers' flag-in-data slots from the epilogue."""
     out = _run(2, 29611)
     print(out[-1500:])
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("env", [dict(NM_HALO_OVERLAP="0"), dict(NM_P2P="0")])
+@pytest.mark.parametrize("env", [dict(NM_SLAB_PERS="0"), dict(NM_SLAB_PERS="0", NM_HALO_OVERLAP="0"), dict(NM_P2P="0")])
 def test_two_ranks_blocking_exchange_and_nccl_fallback(env):
-    """The blocking peer-window exchange (flags awaited in k_halo_push) and the NCCL send/recv fallback."""
+    """Per-step launches with the overlapped peer-window exchange (flags polled by the step kernel), the blocking
+    exchange (flags awaited in k_halo_push) and the NCCL send/recv fallback."""
     out = _run(2, 29615, env_extra=dict(env, NM_MP_CASES="prem3k_p1_j2"))
     print(out[-800:])
 
@@ -46,9 +47,9 @@ def test_all_ranks_halo_exchange_and_solve():
     print(out[-1500:])
 
 
-@pytest.mark.skipif(_ngpu() < 2 or os.environ.get("NM_TEST_FUSED") != "1",
-                    reason="needs >= 2 GPUs and NM_TEST_FUSED=1 (fused step: written after round 1's last GPU run, not validated yet)")
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
 def test_two_ranks_fused_step():
-    """NM_HALO_FUSED=1: boundary rows stored to the peers from the step kernel's epilogue, no kernel between steps."""
-    out = _run(2, 29617, env_extra=dict(NM_HALO_FUSED="1"))
+    """NM_HALO_FUSED=1 (per-step launches): boundary rows stored to the peers from the step kernel's epilogue, arrival
+    flags raised by the grid's last consumer warp, no kernel between steps."""
+    out = _run(2, 29617, env_extra=dict(NM_HALO_FUSED="1", NM_SLAB_PERS="0", NM_MP_CASES="prem3k_p1_j2"))
     print(out[-800:])

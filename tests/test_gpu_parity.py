@@ -370,7 +370,10 @@ def test_packed_kernel_ring_and_chunking(nm, monkeypatch, sell, entries, distinc
     nm.nm_parcsr_free(h)
 
 
-SLAB_CONFIGS = [dict(), dict(NM_SLAB_WS="0"), dict(NM_SLAB_THREADS="64", NM_SLAB_STAGES="3"),
+SLAB_CONFIGS = [dict(), dict(NM_SLAB_PERS="0"), dict(NM_SLAB_PERS_STAGES="2"), dict(NM_SLAB_PERS_STAGES="3", NM_SLAB_MAXGRID="5"),
+                dict(NM_SLAB_PERS_STAGES="4", NM_SLAB_ENTRIES="200", NM_SLAB_DISTINCT="140", NM_SLAB_MAXGRID="3", NM_SLAB_XS="3"),
+                dict(NM_SLAB_THREADS="64", NM_SLAB_ENTRIES="96", NM_SLAB_DISTINCT="140", NM_SLAB_MAXGRID="1", NM_SLAB_PERS_STAGES="2"),
+                dict(NM_SLAB_WS="0"), dict(NM_SLAB_THREADS="64", NM_SLAB_STAGES="3"),
                 dict(NM_SLAB_THREADS="128", NM_SLAB_SPLIT="32", NM_SLAB_STAGES="4", NM_SLAB_XS="2", NM_SLAB_PRODUCERS="1"),
                 dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="8", NM_SLAB_PRODUCERS="8"), dict(NM_SLAB_PRODUCERS="2", NM_SLAB_PDL="0"), dict(NM_SLAB_STAGES="3", NM_SLAB_XS="3"),
                 dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="4", NM_SLAB_MAXGRID="2"),
@@ -394,7 +397,8 @@ def test_chebiter_slab_kernel_configs(nm, monkeypatch, cfg):
     from normalmodes_b200._lib import check, dptr
     for k, v in cfg.items():
         monkeypatch.setenv(k, v)
-    want = dict(pack=1, sell=2).get(cfg.get("NM_CHEB_KERNEL", "slab"), 3 if cfg.get("NM_SLAB_WS") == "0" else 4)
+    want = dict(pack=1, sell=2).get(cfg.get("NM_CHEB_KERNEL", "slab"),
+                                    3 if cfg.get("NM_SLAB_WS") == "0" else (4 if cfg.get("NM_SLAB_PERS") == "0" else 5))
     for name, key, sign in (("const3k_p2_j1", "B", 1.0), ("prem3k_p1_j2", "B", 1.0), ("prem3k_p2_j2", "Ap", -1.0)):
         c = load_case(name)
         m = to_coomat(c["mats"])[key]
@@ -404,7 +408,7 @@ def test_chebiter_slab_kernel_configs(nm, monkeypatch, cfg):
         ref, _ = fem.jacobi_scale(c["mats"][key], sign)
         St = fem.to_scipy(ref)
         lb, ub = 0.2, 4.5
-        for deg in (1, 2, 9):
+        for deg in (1, 2, 9, 30):
             cheb = mv.chebiter_setup(lb, ub, deg, h)
             kind = C.c_int(); nb = C.c_longlong()
             check(nm.nm_chebiter_pack_info(cheb, C.byref(kind), C.byref(nb)))
