@@ -91,6 +91,9 @@ int nm_pol_info(void* pol, int* deg, double* cc, double* dd, double* gam, double
 int nm_pol_coeffs(void* pol, double* mu /* deg+1 */);
 int nm_pol_free(void* pol);
 int nm_tridiag_eig_host(int k, const double* d, const double* e, double* w, double* Z, double* lastrow);
+/* dense symmetric-definite pencil H c = w G c (m x m, column-major; Cholesky + cyclic Jacobi): the Rayleigh-Ritz
+ * refinement of the accepted eigenvectors; host only */
+int nm_sym_geneig_host(int m, const double* H, const double* G, double* w, double* C);
 
 /* ---- FE assembly: cg_create_matrix (mod_cg_create_matrix.f90:35-61) ----
  * nm_fem_create  = topology + DOF numbering + CSR patterns on the host (matrixstruct :1269-1455,
@@ -137,6 +140,10 @@ int nm_pevsl_get_nev(void* pevsl, int* nev);
 int nm_pevsl_copy_result(void* pevsl, double* vals, double* vecs, int ld, double* res /* may be NULL */);
 int nm_pevsl_stats(void* pevsl, int* steps, int* deg, double* t_total, double* t_filter, double* t_reorth,
                    double* t_ritz, long long* n_filter);
+/* diagnostic: microseconds of the dense kernels of the Lanczos phase on random data of local length n -- one CGS pass
+ * over k basis columns (us[0] c = V^T z incl. the partial reduction, us[1] z -= Z c), us[2] the Ritz product U = V S
+ * (k x ns, DMMA), us[3] the Gram block U^T U (ns x ns, DMMA) */
+int nm_diag_lanczos_kernels(long long n, int k, int ns, double* us4);
 /* one application y = p(A B^-1) z of the polynomial filter (ChebAv), the unit of the headline metric */
 int nm_pevsl_filter_host(void* pevsl, void* pol, const double* z, double* y);
 int nm_pevsl_filter_dev(void* pevsl, void* pol, const double* z_dev, double* y_dev, double* work3n_dev);

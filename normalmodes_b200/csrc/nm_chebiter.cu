@@ -83,7 +83,6 @@ static void cheb_build_ppack(NmChebIter& C) {
           }
       for (int row = 0; row < n && sym; ++row) sym = sent[row] == needs[row];
     }
-    const bool fused = sym && nm_env_int("NM_HALO_FUSED", 0) != 0;
     C.pers_multi_ok = sym;
     for (int& v : sidx) v = R * newid[v / R] + v % R;
     C.send_idx_p.from_host(sidx);
@@ -104,35 +103,41 @@ static void cheb_build_ppack(NmChebIter& C) {
         }
       C.push_off.from_host(cnt);
       C.push_ent.alloc(std::max<size_t>(ent.size(), 1)); C.push_ent.upload(ent.data(), ent.size());
-      C.fused = fused;
     }
   }
 }
 
-// Persistent kernel (k_slabpers): stages per CTA from the shared memory left beside the co-resident CTAs of an SM,
-// Chebyshev coefficients and the grid-barrier counter on the device, flag-in-data ghost slots on several GPUs.
-static void cheb_setup_pers(NmChebIter& C) {
+// In-kernel halo on several GPUs (collective decision, every rank takes the same branch) and the opt-in persistent
+// kernel (k_slabpers, NM_SLAB_PERS=1): stages per CTA from the shared memory left beside the co-resident CTAs of an
+// SM, Chebyshev coefficients and the grid-barrier counter on the device.
+static void cheb_setup_multi_pers(NmChebIter& C) {
   NmParcsr& M = *C.M;
   NmCtx& c = nm_ctx();
   NmSlab& S = C.pslab;
-  C.pers = false;
-  const bool want = nm_env_int("NM_SLAB_PERS", 1) != 0 && S.nchunk > 0 && S.ws && S.max_chunks_per_cta <= NM_SLAB_MAXDESC;
-  // collective part first: every rank takes the same branch (the halo plan exists on all ranks or on none)
-  bool multi_ok = true;
+  C.pers = false; C.fused = false;
+  const bool slab_ok = S.nchunk > 0 && S.ws;
+  bool ll_ok = true;
   if (c.nranks > 1) {
-    double v = (want && (M.halo.nsend == 0 || C.pers_multi_ok) && (M.halo.nghost == 0) == (M.halo.nsend == 0)) ? 1.0 : 0.0;
-    if (!c.p2p) v = 0.0;
+    double v = (slab_ok && (M.halo.nsend == 0 || C.pers_multi_ok) && (M.halo.nghost == 0) == (M.halo.nsend == 0)) ? 1.0 : 0.0;
+    if (!c.p2p || nm_env_int("NM_HALO_FUSED", 1) == 0) v = 0.0;
     DBuf<double> d(1);
     d.upload(&v, 1);
     NM_NCCL(ncclAllReduce(d.p, d.p, 1, ncclDouble, ncclMin, c.nccl, c.stream));
     d.download(&v, 1);
-    multi_ok = v > 0.5;
-    if (multi_ok) multi_ok = nm_halo_ll_setup(M.halo);
+    ll_ok = v > 0.5;
+    if (ll_ok) ll_ok = nm_halo_ll_setup(M.halo);
+    C.fused = ll_ok;
   }
-  if (!want || !multi_ok) return;
+  // NM_SLAB_PERS: 0 (default) one launch per step chained by programmatic dependent launch; 1 the whole iteration in one
+  // cooperative launch.  Measured on the bench workload (profiles/r2c_*): the software grid barrier (fence + atomic,
+  // poll + fence) costs 2-4 us per step more than the hardware's grid completion + dependent launch, and the dataflow
+  // variant (NM_SLAB_FLOW=1: per-chunk flags instead of the barrier) another 7-10 us (a serial poll + fence per chunk
+  // visit in the producers) -- kept as tested options, not the default.
+  const bool want = nm_env_int("NM_SLAB_PERS", 0) != 0 && slab_ok && S.max_chunks_per_cta <= NM_SLAB_MAXDESC;
+  if (!want || !ll_ok) return;
   const int per_sm = std::max(1, nm_div_up(S.grid, c.sm_count));
   const int budget = std::min(227 * 1024, (228 * 1024) / per_sm - 1024);
-  const int fixed = (int)((NM_SLAB_MAXDESC * sizeof(NmPackDesc) + 256 + 8 * (size_t)S.nxs * S.xs_doubles + 15) & ~(size_t)15);
+  const int fixed = (int)((NM_SLABPERS_FIXED + 8 * (size_t)S.nxs * S.xs_doubles + 15) & ~(size_t)15);
   int nst = (budget - fixed) / std::max(S.stage_bytes, 16);
   nst = std::max(0, std::min(8, std::min(nst, nm_env_int("NM_SLAB_PERS_STAGES", 8))));
   if (nst < 2) return;
@@ -143,43 +148,31 @@ static void cheb_setup_pers(NmChebIter& C) {
   C.pers = true;
 }
 
-// One step of the fused multi-GPU iteration: kernel k polls the flags of the values it gathers (pushed by the peers'
-// step k-1, or by the explicit push of b before step 0) and stores its own new direction into the peers' windows.
-static void cheb_step_fused(NmChebIter& C, const double* din, const EpiCheb& e, int k, NmHaloWait& poll) {
+// One step of the fused multi-GPU iteration: kernel k polls the flag-in-data slots of the ghost values it gathers
+// (written by the peers' step k-1, or by nm_halo_push_ll of b before step 0) and stores its own new direction into the
+// peers' slots of the next tag.
+static void cheb_step_fused(NmChebIter& C, const double* din, const EpiCheb& e, int k, unsigned tag0) {
   NmParcsr& M = *C.M;
   NmHalo& h = M.halo;
   NmCtx& c = nm_ctx();
-  if (k == 0) {
-    const bool ok = nm_halo_push_nowait(M, din, C.send_idx_p.p, &poll);
-    NM_REQUIRE(ok, "fused step without a peer window");
-  }
   NmSlabFusedArgs F;
   memset(&F, 0, sizeof(F));
-  NmHaloWait next;
-  next.flags = nullptr; next.mask = 0; next.epoch = 0; next.status = nullptr;
-  double* next_xg = nullptr;
-  if (k < C.deg - 1) {
-    const unsigned long long epoch = ++h.epoch;
-    const int par = (int)(epoch & 1);
-    F.push_off = C.push_off.p; F.push_ent = C.push_ent.p;
-    for (int r = 0; r < c.nranks; ++r) {
-      if (r == c.rank) continue;
-      if (h.send_cnt[r] > 0) F.peer_xg[r] = (double*)(c.peer_win[r] + h.peer_xg[par][r]);   // NmPushEnt::dst already includes peer_base
-      if (h.send_cnt[r] > 0 || h.recv_cnt[r] > 0) {                       // flags both ways on every link (nm_parcsr.cu)
-        F.send_mask |= 1u << r;
-        F.peer_flag[r] = (unsigned long long*)(c.peer_win[r] + h.peer_flag[r]) + c.rank;
-        next.mask |= 1u << r;
-      }
+  if (h.nsend > 0) {
+    const unsigned tin = tag0 + (unsigned)k;
+    F.ll_in = (const unsigned long long*)(c.win + h.win_ll[tin % 3u]);
+    F.tag_in = tin; F.status = c.dev_status;
+    static const int dbg = nm_env_int("NM_DEBUG_LL", 0);
+    F.debug = dbg;
+    if (k < C.deg - 1) {
+      F.tag_out = tin + 1u;
+      F.push_off = C.push_off.p; F.push_ent = C.push_ent.p;
+      for (int r = 0; r < c.nranks; ++r)
+        if (r != c.rank && h.send_cnt[r] > 0) F.ll_out[r] = (unsigned long long*)(c.peer_win[r] + h.peer_ll[F.tag_out % 3u][r]);
     }
-    F.push_epoch = epoch;
-    F.ctr = c.push_ctr + 8;
-    next.flags = (const unsigned long long*)(c.win + h.win_flag);
-    next.epoch = epoch; next.status = c.dev_status;
-    next_xg = (double*)(c.win + h.win_xg[par]);
   }
-  nm_slabws_dispatch<true>(M, C.pslab, din, e, poll, F);
-  if (next_xg) h.xg_cur = next_xg;
-  poll = next;
+  NmHaloWait none;
+  none.flags = nullptr; none.mask = 0; none.epoch = 0; none.status = nullptr;
+  nm_slabws_dispatch<true>(M, C.pslab, din, e, none, F);
 }
 
 NmChebIter* nm_chebiter_build(double lb, double ub, int deg, NmParcsr* M) {
@@ -201,7 +194,7 @@ NmChebIter* nm_chebiter_build(double lb, double ub, int deg, NmParcsr* M) {
   const size_t n = M->nrow > 0 ? M->nrow : 1;
   C->r.alloc(n); C->d0.alloc(n); C->d1.alloc(n);
   cheb_build_ppack(*C);
-  cheb_setup_pers(*C);
+  cheb_setup_multi_pers(*C);
   return C.release();
 }
 
@@ -236,6 +229,9 @@ void nm_chebiter_solve(NmChebIter& C, const double* b, double* x) {
     W.b = b; W.r = C.r.p; W.d0 = C.d0.p; W.d1 = C.d1.p; W.xout = x;
     W.ak = C.ak_dev.p; W.bk = C.bk_dev.p; W.inv_theta = 1.0 / C.theta;
     W.gbar = C.gbar.p; W.gbase = C.gbar_base;
+    static const bool want_flow = nm_env_int("NM_SLAB_FLOW", 1) != 0;
+    const bool flow = want_flow && S.deps_ok;
+    if (flow) { W.cflag = S.cflag.p; W.desc_cid = S.desc_cid.p; W.ftag0 = C.ftag; }
     NmHalo& h = M.halo;
     if (c.nranks > 1 && h.nsend > 0) {
       const unsigned long long e0 = ++h.epoch;
@@ -261,7 +257,8 @@ void nm_chebiter_solve(NmChebIter& C, const double* b, double* x) {
       launched = false;
     }
     if (launched) {
-      C.gbar_base += (unsigned long long)(C.deg - 1) * (unsigned long long)S.grid;
+      if (flow) C.ftag += (unsigned)C.deg;
+      else C.gbar_base += (unsigned long long)(C.deg - 1) * (unsigned long long)S.grid;
       k_perm_scatter<<<nm_div_up(M.nrow, 256), 256, 0, c.stream>>>(xout, C.xp.p, order_dev, nblk, R);
       c.launches++;
       C.nsolve++;
@@ -270,8 +267,14 @@ void nm_chebiter_solve(NmChebIter& C, const double* b, double* x) {
     }
   }
   const double* din = b;
-  NmHaloWait fused_poll;
-  fused_poll.flags = nullptr; fused_poll.mask = 0; fused_poll.epoch = 0; fused_poll.status = nullptr;
+  unsigned fused_tag0 = 0;
+  if (C.fused && M.halo.nsend > 0) {
+    // boundary values of b -> the peers' slots (what step 0 gathers); deg epochs for the solve
+    const unsigned long long e0 = ++M.halo.epoch;
+    fused_tag0 = (unsigned)e0;
+    nm_halo_push_ll(M, b, C.send_idx_p.p, fused_tag0, (int)(fused_tag0 % 3u));
+    M.halo.epoch = e0 + (unsigned long long)(C.deg - 1);
+  }
   for (int k = 0; k < C.deg; ++k) {
     EpiCheb e;
     e.first = (k == 0); e.last = (k == C.deg - 1);
@@ -281,7 +284,7 @@ void nm_chebiter_solve(NmChebIter& C, const double* b, double* x) {
     e.d_out = dbuf[k & 1];
     e.x = x;
     e.inv_theta = 1.0 / C.theta; e.ak = C.ak[k]; e.bk = C.bk[k];
-    if (C.fused) cheb_step_fused(C, din, e, k, fused_poll);
+    if (C.fused) cheb_step_fused(C, din, e, k, fused_tag0);
     else if (C.pslab.nchunk > 0) nm_spmv_slab_epi(M, C.pslab, din, e, C.send_idx_p.p);
     else if (C.psell.nchunk > 0) nm_spmv_sell_epi(M, C.psell, din, e, C.send_idx_p.p);
     else if (perm) nm_spmv_pack_epi(M, C.ppack, din, e, C.send_idx_p.p);

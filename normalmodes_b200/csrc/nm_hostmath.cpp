@@ -98,6 +98,96 @@ int nm_tridiag_eig(int k, const double* d, const double* e, double* w, double* Z
   return nm_tridiag_eig_ex(k, d, e, w, Z, nullptr);
 }
 
+// ---------------------------------------------------------------- small dense symmetric-definite pencil
+// H c = w G c for the Rayleigh-Ritz refinement of the accepted Ritz vectors (nm_lanczos.cu): H, G are m x m,
+// column-major, symmetric, G ~ I (the vectors are B-orthonormal to rounding) and H nearly diagonal (they are nearly
+// eigenvectors) -- the case where the cyclic Jacobi method converges in two or three sweeps and is as accurate as
+// anything (the image has no LAPACK).  G = L L^T (Cholesky), H' = L^-1 H L^-T, Jacobi on H', C = L^-T C'.
+// Output: w ascending, C column-major with C^T G C = I.  Returns 0, 1 (G not positive definite) or 2 (no convergence).
+int nm_sym_geneig(int m, const double* Hin, const double* Gin, double* w, double* C) {
+  if (m <= 0) return 0;
+  const size_t M = (size_t)m;
+  std::vector<double> L(M * M, 0.0), A(M * M);
+  for (int j = 0; j < m; ++j)                                   // Cholesky, lower, column by column
+    for (int i = j; i < m; ++i) {
+      double sum = 0.5 * (Gin[i + j * M] + Gin[j + i * M]);
+      for (int k = 0; k < j; ++k) sum -= L[i + k * M] * L[j + k * M];
+      if (i == j) {
+        if (!(sum > 0.0)) return 1;
+        L[j + j * M] = sqrt(sum);
+      } else {
+        L[i + j * M] = sum / L[j + j * M];
+      }
+    }
+  for (int j = 0; j < m; ++j)
+    for (int i = 0; i < m; ++i) A[i + j * M] = 0.5 * (Hin[i + j * M] + Hin[j + i * M]);
+  for (int j = 0; j < m; ++j)                                   // A <- L^-1 A (forward substitution on every column)
+    for (int i = 0; i < m; ++i) {
+      double sum = A[i + j * M];
+      for (int k = 0; k < i; ++k) sum -= L[i + k * M] * A[k + j * M];
+      A[i + j * M] = sum / L[i + i * M];
+    }
+  for (int i = 0; i < m; ++i)                                   // A <- A L^-T (the same on every row)
+    for (int j = 0; j < m; ++j) {
+      double sum = A[i + j * M];
+      for (int k = 0; k < j; ++k) sum -= A[i + k * M] * L[j + k * M];
+      A[i + j * M] = sum / L[j + j * M];
+    }
+  for (int j = 0; j < m; ++j)
+    for (int i = 0; i < j; ++i) { const double t = 0.5 * (A[i + j * M] + A[j + i * M]); A[i + j * M] = A[j + i * M] = t; }
+  std::vector<double> V(M * M, 0.0);
+  for (int i = 0; i < m; ++i) V[i + i * M] = 1.0;
+  // rotate (p, q) only while |a_pq| > eps sqrt(|a_pp a_qq|) (the relative criterion that gives small eigenvalues to
+  // full relative accuracy); converged when a whole sweep rotates nothing
+  bool converged = false;
+  const double eps = 2.220446049250313e-16;
+  for (int sweep = 0; sweep < 60 && !converged; ++sweep) {
+    long rotations = 0;
+    for (int p = 0; p < m - 1; ++p)
+      for (int q = p + 1; q < m; ++q) {
+        const double apq = A[p + q * M];
+        const double app = A[p + p * M], aqq = A[q + q * M];
+        if (fabs(apq) <= eps * sqrt(fabs(app * aqq))) { A[p + q * M] = A[q + p * M] = 0.0; continue; }
+        ++rotations;
+        const double theta = (aqq - app) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < m; ++k) {                            // columns p, q
+          const double akp = A[k + p * M], akq = A[k + q * M];
+          A[k + p * M] = c * akp - sn * akq;
+          A[k + q * M] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < m; ++k) {                            // rows p, q
+          const double apk = A[p + k * M], aqk = A[q + k * M];
+          A[p + k * M] = c * apk - sn * aqk;
+          A[q + k * M] = sn * apk + c * aqk;
+        }
+        A[p + q * M] = A[q + p * M] = 0.0;
+        for (int k = 0; k < m; ++k) {
+          const double vkp = V[k + p * M], vkq = V[k + q * M];
+          V[k + p * M] = c * vkp - sn * vkq;
+          V[k + q * M] = sn * vkp + c * vkq;
+        }
+      }
+    converged = rotations == 0;
+  }
+  if (!converged) return 2;
+  for (int j = 0; j < m; ++j)                                   // V <- L^-T V (back substitution)
+    for (int i = m - 1; i >= 0; --i) {
+      double sum = V[i + j * M];
+      for (int k = i + 1; k < m; ++k) sum -= L[k + i * M] * V[k + j * M];
+      V[i + j * M] = sum / L[i + i * M];
+    }
+  std::vector<int> idx(m);
+  std::iota(idx.begin(), idx.end(), 0);
+  std::sort(idx.begin(), idx.end(), [&](int a, int b) { return A[a + a * M] < A[b + b * M]; });
+  for (int j = 0; j < m; ++j) {
+    w[j] = A[idx[j] + idx[j] * M];
+    std::copy(V.begin() + idx[j] * M, V.begin() + (idx[j] + 1) * M, C + j * M);
+  }
+  return 0;
+}
+
 // ---------------------------------------------------------------- find_pol
 static void dampcf(int m, int damping, std::vector<double>& jac) {
   jac.assign(m + 1, 1.0);
@@ -200,6 +290,13 @@ extern "C" int nm_tridiag_eig_host(int k, const double* d, const double* e, doub
   NM_API_BEGIN
   int rc = nm_tridiag_eig_ex(k, d, e, w, Z, lastrow);
   NM_REQUIRE(rc == 0, "tridiagonal QL failed to converge for eigenvalue %d", rc - 1);
+  NM_API_END
+}
+
+extern "C" int nm_sym_geneig_host(int m, const double* H, const double* G, double* w, double* Cout) {
+  NM_API_BEGIN
+  int rc = nm_sym_geneig(m, H, G, w, Cout);
+  NM_REQUIRE(rc == 0, "dense symmetric-definite eigensolver failed (%s)", rc == 1 ? "G not positive definite" : "Jacobi did not converge");
   NM_API_END
 }
 

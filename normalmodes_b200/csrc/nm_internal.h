@@ -72,7 +72,8 @@ struct NmCtx {
 NmCtx& nm_ctx();
 void nm_ensure_init();
 double* nm_red_scratch(size_t n);
-size_t nm_win_alloc(size_t bytes);          // bump allocation in the peer window (256-byte aligned), collective order
+size_t nm_win_alloc(size_t bytes);          // slot in the peer window (256-byte granules, zeroed), collective order
+void nm_win_free(size_t off, size_t bytes);
 void nm_check_device_status();              // raises if a device-side wait timed out
 double* nm_pinned(size_t n);
 
@@ -138,6 +139,16 @@ struct NmHalo {
   bool ll = false;
   size_t win_ll[3] = {0, 0, 0};
   std::vector<size_t> peer_ll[3];
+  NmHalo() {}
+  NmHalo(const NmHalo&) = delete;
+  NmHalo& operator=(const NmHalo&) = delete;
+  ~NmHalo() {                               // hand the window slots back (nm_parcsr_free / nm_op_free)
+    if (p2p) {
+      const size_t gb = (size_t)(nghost > 0 ? nghost : 1) * sizeof(double);
+      nm_win_free(win_xg[0], gb); nm_win_free(win_xg[1], gb); nm_win_free(win_flag, sizeof(unsigned long long) * 8);
+    }
+    if (ll) for (int b = 0; b < 3; ++b) nm_win_free(win_ll[b], 16 * (size_t)(nghost > 0 ? nghost : 1));
+  }
 };
 
 // Packed row-block format of the streaming SpMV (nm_spmv.cuh / nm_pack.cu).  The (block-)rows are ordered for
@@ -191,6 +202,11 @@ struct NmSlabHeader { int nr, nd, nslice, first, nep, gmax, has_ghost, pad2; }; 
 struct NmSlab {
   // persistent kernel (k_slabpers): stages per CTA when the whole iteration runs in one cooperative launch
   int pers_nstage = 0, pers_smem = 0;
+  // dataflow execution: chunk id of every descriptor, per-chunk completion flags (epoch of the last finished step);
+  // the ids of the chunks a chunk depends on sit at the end of its blob (header word 7 = their number)
+  DBuf<int> desc_cid;
+  DBuf<unsigned> cflag;
+  bool deps_ok = false;
   DBuf<unsigned char> blob;
   DBuf<NmPackDesc> desc;
   DBuf<int> cta_first;                    // grid+1: first chunk of each CTA (balanced by bytes)
@@ -257,6 +273,7 @@ struct NmChebIter {
   DBuf<double> ak_dev, bk_dev;
   DBuf<unsigned long long> gbar;          // grid-barrier counter of the persistent kernel (monotonic)
   unsigned long long gbar_base = 0;
+  unsigned ftag = 0;                      // dataflow: chunk-flag epoch consumed so far (a solve uses deg of them)
   long long nsolve = 0, nmatvec = 0;
   double t_total = 0;
 };
@@ -362,6 +379,7 @@ void nm_filter_update(const double* vkm1, double* vout, const double* vk, const 
 // host maths
 int nm_tridiag_eig(int k, const double* d, const double* e, double* w, double* Z /* k*k col-major or null */);
 int nm_tridiag_eig_ex(int k, const double* d, const double* e, double* w, double* Z, double* lastrow);
+int nm_sym_geneig(int m, const double* H, const double* G, double* w, double* C);   // dense H c = w G c (Cholesky + Jacobi)
 void nm_findpol(const double xintv[4], double thresh_int, double thresh_ext, NmPol& pol);
 // solver
 void nm_lanbounds(NmPevsl& P, int mlan, int lanstep, double tol, double* lmin, double* lmax);

@@ -213,6 +213,74 @@ static void ritz_vectors(Basis& V, int kdim, const double* S_dev, int lds, int n
   }
 }
 
+// ---------------------------------------------------------------- Gram blocks G = X^T Y on fp64 tensor cores
+// The block inner products of the Rayleigh-Ritz refinement (and of any block orthogonalisation): X (n x p) and
+// Y (n x q) column-major with leading dimension n, G (p x q) column-major.  A real dense contraction with the long
+// dimension n as the MMA's k: mma.sync m8n8k4 f64, A fragment = 4 consecutive rows of 8 columns of X (each lane one
+// double, 4 lanes = one 32-byte sector), B fragment likewise from Y; a CTA of 4 warps owns a 32 x 32 tile of G over one
+// of GR_SLABS row slabs, partial tiles are summed over the slabs in a fixed order (deterministic, no fp64 atomics).
+#define GR_SLABS 64
+__global__ void __launch_bounds__(128)
+k_gram_dmma(const double* __restrict__ X, const double* __restrict__ Y, size_t n, int p, int q, double* __restrict__ partial) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tg = lane & 3;
+  const int i0 = blockIdx.y * 32 + (warp >> 1) * 16, j0 = blockIdx.z * 32 + (warp & 1) * 16;
+  const size_t rows_per = ((n + GR_SLABS - 1) / GR_SLABS + 3) & ~(size_t)3;
+  const size_t r0 = (size_t)blockIdx.x * rows_per, r1 = r0 + rows_per < n ? r0 + rows_per : n;
+  double acc[2][2][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  const double* xa[2]; const double* yb[2];
+  bool xok[2], yok[2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a) { const int col = i0 + 8 * a + g; xok[a] = col < p; xa[a] = X + (size_t)(xok[a] ? col : 0) * n; }
+#pragma unroll
+  for (int b = 0; b < 2; ++b) { const int col = j0 + 8 * b + g; yok[b] = col < q; yb[b] = Y + (size_t)(yok[b] ? col : 0) * n; }
+  for (size_t r = r0; r < r1; r += 4) {
+    const size_t rr = r + tg;
+    const bool in = rr < r1;
+    double af[2], bf[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) af[a] = (in && xok[a]) ? xa[a][rr] : 0.0;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) bf[b] = (in && yok[b]) ? yb[b][rr] : 0.0;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+  }
+  double* out = partial + (size_t)blockIdx.x * p * q;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int gi = i0 + 8 * a + g, gj = j0 + 8 * b + 2 * tg + e;
+        if (gi < p && gj < q) out[(size_t)gj * p + gi] = acc[a][b][e];
+      }
+}
+__global__ void k_gram_reduce(const double* __restrict__ partial, size_t pq, double* __restrict__ G) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= pq) return;
+  double s = 0.0;
+  for (int t = 0; t < GR_SLABS; ++t) s += partial[(size_t)t * pq + i];
+  G[i] = s;
+}
+// G_dev (p x q, column-major) = X^T Y, summed over the ranks
+static void gram(const double* X, const double* Y, size_t n, int p, int q, double* G_dev) {
+  NmCtx& ctx = nm_ctx();
+  const size_t pq = (size_t)p * q;
+  double* partial = nm_red_scratch((size_t)GR_SLABS * pq);
+  dim3 grid(GR_SLABS, nm_div_up(p, 32), nm_div_up(q, 32));
+  k_gram_dmma<<<grid, 128, 0, ctx.stream>>>(X, Y, n, p, q, partial);
+  k_gram_reduce<<<nm_div_up((long long)pq, 256), 256, 0, ctx.stream>>>(partial, pq, G_dev);
+  ctx.launches += 2;
+  nm_allreduce_sum(G_dev, pq);
+}
+
 // out = a*x  (scale-copy)
 __global__ void k_scale_copy(double* out, const double* x, double a, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -233,25 +301,38 @@ void nm_lanbounds(NmPevsl& P, int mlan, int lanstep, double tol, double* lmin_ou
   const bool gen = P.geneig;
   if (gen) NM_REQUIRE(P.bsol && P.B, "lanbounds: generalised problem needs setbmv + setbsol_chebiter");
   const size_t n = P.n;
-  const int m = std::max(2, std::min(std::min(mlan, lanstep), P.N));
+  const int m = std::max(2, std::min(std::min(mlan, lanstep), P.N));       // operator applications at most
+  // Basis columns kept at most: pEVSL's LanTrbounds is a thick-restart Lanczos with mlan basis vectors; the full basis of
+  // a 2 M-tet mesh (67 MB per column, V and Z in the generalised case) must not be allowed to grow to mlan = 3000
+  // columns.  When the cap is reached the iteration restarts from the sum of the two extreme Ritz vectors (explicit
+  // restart: the new Krylov space starts where the old one's extremes were), a quarter of the free memory at most.
+  size_t free_b = 0, total_b = 0;
+  NM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  long long cap_ll = (long long)(free_b / 4) / (long long)(8 * std::max<size_t>(n, 1) * (gen ? 2 : 1));
+  int cap = (int)std::max(32ll, std::min((long long)m, cap_ll));
+  cap = std::max(8, std::min(cap, nm_env_int("NM_LANBOUNDS_MAXCOLS", cap)));
   Basis V, Z;
   V.init(n); Z.init(n);
   Basis& Zr = gen ? Z : V;
-  DBuf<double> w(std::max<size_t>(n, 1)), cbuf(m + 1);
+  DBuf<double> w(std::max<size_t>(n, 1)), cbuf(cap + 2);
   std::vector<double> dT, eT, th, lr;
-  // start vector
+  auto normalise_start = [&]() {
+    if (gen) {
+      nm_op_apply(*P.B, V.col(0), Z.col(0));
+      const double t = 1.0 / sqrt(nm_vec_dot(V.col(0), Z.col(0), n));
+      nm_vec_scale(V.col(0), t, n); nm_vec_scale(Z.col(0), t, n);
+    } else {
+      const double t = 1.0 / sqrt(nm_vec_dot(V.col(0), V.col(0), n));
+      nm_vec_scale(V.col(0), t, n);
+    }
+  };
   nm_vec_random(V.col(0), n, P.seed + 17, (unsigned long long)(P.nfirst >= 0 ? P.nfirst : 0));
-  if (gen) {
-    nm_op_apply(*P.B, V.col(0), Z.col(0));
-    const double t = 1.0 / sqrt(nm_vec_dot(V.col(0), Z.col(0), n));
-    nm_vec_scale(V.col(0), t, n); nm_vec_scale(Z.col(0), t, n);
-  } else {
-    const double t = 1.0 / sqrt(nm_vec_dot(V.col(0), V.col(0), n));
-    nm_vec_scale(V.col(0), t, n);
-  }
+  normalise_start();
   double lmin = 0, lmax = 0, beta = 0;
+  bool breakdown = false;
   const int check_every = 10;
-  for (int k = 0; k < m; ++k) {
+  int k = 0;                                                    // column of the current basis
+  for (int step = 0; step < m; ++step) {
     double* v = V.col(k);
     double* znew = gen ? Z.col(k + 1) : w.p;
     nm_op_apply(*P.A, v, znew);
@@ -263,23 +344,41 @@ void nm_lanbounds(NmPevsl& P, int mlan, int lanstep, double tol, double* lmin_ou
       double* vnew = V.col(k + 1);
       nm_chebiter_solve(*P.bsol, znew, vnew);
       beta = sqrt(fabs(nm_vec_dot(vnew, znew, n)));
-      NM_REQUIRE(beta > 0 && std::isfinite(beta), "lanbounds: breakdown (beta = %g) at step %d", beta, k);
+      NM_REQUIRE(beta > 0 && std::isfinite(beta), "lanbounds: breakdown (beta = %g) at step %d", beta, step);
       nm_vec_scale(vnew, 1.0 / beta, n); nm_vec_scale(znew, 1.0 / beta, n);
     } else {
       beta = sqrt(nm_vec_dot(znew, znew, n));
-      NM_REQUIRE(std::isfinite(beta), "lanbounds: non-finite beta at step %d", k);
-      if (beta == 0.0) { eT.push_back(0.0); break; }
-      scale_copy(V.col(k + 1), znew, 1.0 / beta, n);
+      NM_REQUIRE(std::isfinite(beta), "lanbounds: non-finite beta at step %d", step);
+      // exact breakdown (invariant subspace: B~ = I from a lumped mass matrix, a tiny matrix, ...): the Ritz values of
+      // the T built so far are exact eigenvalues -- fall through to the bounds with r1 = r2 = 0 instead of skipping them
+      breakdown = beta <= 1e-300 || beta * beta <= 1e-30 * fabs(alpha) * fabs(alpha);
+      if (!breakdown) scale_copy(V.col(k + 1), znew, 1.0 / beta, n);
+      else beta = 0.0;
     }
     eT.push_back(beta);
-    const int kk = k + 1;
-    if (kk % check_every && kk != m) continue;
+    const int kk = ++k;
+    const bool last = step == m - 1, full = kk == cap && !last;
+    if (!breakdown && !full && kk % check_every && !last) continue;
     th.resize(kk); lr.resize(kk);
-    int rc = nm_tridiag_eig_ex(kk, dT.data(), eT.data(), th.data(), nullptr, lr.data());
+    std::vector<double> S;
+    if (full) S.resize((size_t)kk * kk);
+    int rc = nm_tridiag_eig_ex(kk, dT.data(), eT.data(), th.data(), full ? S.data() : nullptr, lr.data());
     NM_REQUIRE(rc == 0, "lanbounds: tridiagonal eigensolver failed");
     const double r1 = fabs(beta * lr[0]), r2 = fabs(beta * lr[kk - 1]);
     lmin = th[0] - r1; lmax = th[kk - 1] + r2;
-    if (r1 + r2 < tol * (fabs(lmin) + fabs(lmax))) break;
+    if (breakdown || r1 + r2 < tol * (fabs(lmin) + fabs(lmax))) break;
+    if (full) {
+      // explicit restart: v0 <- y_min + y_max (Ritz vectors of the two ends), normalised; T starts over
+      std::vector<double> comb(kk);
+      for (int i = 0; i < kk; ++i) comb[i] = S[i] + S[(size_t)(kk - 1) * kk + i];
+      DBuf<double> dS(kk);
+      dS.upload(comb.data(), kk);
+      ritz_vectors(V, kk, dS.p, kk, 1, w.p);
+      nm_vec_copy(V.col(0), w.p, n);
+      normalise_start();
+      dT.clear(); eT.clear();
+      k = 0; beta = 0.0;
+    }
   }
   NM_CUDA(cudaStreamSynchronize(nm_ctx().stream));
   nm_check_device_status();
@@ -393,13 +492,18 @@ void nm_cheblannr(NmPevsl& P, const double xintv[4], int maxit, double tol, cons
     for (int c = 0; c < ns; ++c) std::copy(S.begin() + (size_t)sel[c] * kdim, S.begin() + (size_t)(sel[c] + 1) * kdim, Ssel.begin() + (size_t)c * kdim);
     DBuf<double> dS(Ssel.size());
     dS.upload(Ssel.data(), Ssel.size());
-    DBuf<double> U((size_t)ns * std::max<size_t>(n, 1));
+    const size_t nn = std::max<size_t>(n, 1);
+    DBuf<double> U((size_t)ns * nn);
     ritz_vectors(V, kdim, dS.p, kdim, ns, U.p);
-    double* w2 = work.p;
-    double* wk = work.p + n;
-    std::vector<int> keep;
+    V.chunks.clear(); Z.chunks.clear();                         // the Lanczos bases are done: their memory serves A U, B U
+    // accepted pairs: B-normalise, Rayleigh quotient, acceptance in [a, b] (pEVSL ChebLanNr); A u and B u of the
+    // accepted ones are kept (columns nk of AU, BU; u compacted to column nk of U)
+    DBuf<double> AU((size_t)ns * nn), BU((size_t)ns * nn);
+    int nk = 0;
     for (int c = 0; c < ns; ++c) {
       double* u = U.p + (size_t)c * n;
+      double* w2 = BU.p + (size_t)nk * n;
+      double* wk = AU.p + (size_t)nk * n;
       nm_op_apply(*P.B, u, w2);
       double t = sqrt(nm_vec_dot(u, w2, n));
       NM_REQUIRE(t > 0.0, "cheblannr: zero Ritz vector");
@@ -408,18 +512,105 @@ void nm_cheblannr(NmPevsl& P, const double xintv[4], int maxit, double tol, cons
       nm_op_apply(*P.A, u, wk);
       const double lam = nm_vec_dot(wk, u, n);
       if (lam < aa - DBL_EPS_MULT * 2.220446049250313e-16 || lam > bb + DBL_EPS_MULT * 2.220446049250313e-16) continue;
-      nm_vec_axpy(wk, -lam, w2, n);
-      const double res = sqrt(nm_vec_dot(wk, wk, n));
-      keep.push_back(c);
-      P.lam.push_back(lam); P.res.push_back(res);
+      if (c != nk) nm_vec_copy(U.p + (size_t)nk * n, u, n);
+      P.lam.push_back(lam);
+      ++nk;
     }
-    P.nev = (int)keep.size();
-    P.Y.alloc(std::max<size_t>((size_t)P.nev * n, 1));
-    for (int i = 0; i < P.nev; ++i) nm_vec_copy(P.Y.p + (size_t)i * n, U.p + (size_t)keep[i] * n, n);
+    P.nev = nk;
+    P.Y.alloc(std::max<size_t>((size_t)nk * n, 1));
+    const bool refine = nm_env_int("NM_RITZ_REFINE", 1) != 0;
+    bool refined = false;
+    if (nk > 1 && refine) {
+      // Rayleigh-Ritz on the span of the accepted vectors: what is left in a Ritz vector of a non-restarted Lanczos
+      // stopped by the trace test is mostly a mixture of OTHER wanted eigenvectors (multiplet members resolve last);
+      // the nk x nk projected pencil (U^T A U) c = lam (U^T B U) c removes exactly that.  Two Gram blocks and three
+      // n x nk x nk products on the fp64 tensor cores; A U and B U rotate with U, so no further operator applications.
+      DBuf<double> HG((size_t)2 * nk * nk);
+      gram(U.p, AU.p, n, nk, nk, HG.p);
+      gram(U.p, BU.p, n, nk, nk, HG.p + (size_t)nk * nk);
+      std::vector<double> hHG((size_t)2 * nk * nk), w(nk), Cm((size_t)nk * nk);
+      HG.download(hHG.data(), hHG.size());
+      const int rc2 = nm_sym_geneig(nk, hHG.data(), hHG.data() + (size_t)nk * nk, w.data(), Cm.data());
+      if (rc2 == 0 && w[0] >= aa - 1e-8 * fabs(aa) && w[nk - 1] <= bb + 1e-8 * fabs(bb)) {
+        DBuf<double> dC(Cm.size());
+        dC.upload(Cm.data(), Cm.size());
+        auto rotate = [&](DBuf<double>& X, double* out) {       // out = X C  (n x nk by nk x nk)
+          dim3 grid(nm_div_up((long long)n, RG_BM), nm_div_up(nk, RG_BN));
+          k_ritz_gemm<<<grid, 128, 0, ctx.stream>>>(X.p, n, nk, dC.p, nk, nk, out, 0);
+          ctx.launches++;
+        };
+        rotate(U, P.Y.p);
+        DBuf<double> T((size_t)nk * nn);
+        rotate(AU, T.p); std::swap(AU.p, T.p); std::swap(AU.n, T.n);
+        rotate(BU, T.p); std::swap(BU.p, T.p); std::swap(BU.n, T.n);
+        for (int i = 0; i < nk; ++i) P.lam[i] = w[i];
+        refined = true;
+      }
+    }
+    if (!refined)
+      for (int i = 0; i < nk; ++i) nm_vec_copy(P.Y.p + (size_t)i * n, U.p + (size_t)i * n, n);
+    // residuals ||A y - lam B y||_2 from the (rotated) products
+    for (int i = 0; i < nk; ++i) {
+      double* wk = AU.p + (size_t)i * n;
+      nm_vec_axpy(wk, -P.lam[i], BU.p + (size_t)i * n, n);
+      P.res.push_back(sqrt(nm_vec_dot(wk, wk, n)));
+    }
     NM_CUDA(cudaStreamSynchronize(ctx.stream));
   }
   nm_check_device_status();
   P.t_filter = t_filter; P.t_reorth = t_reorth; P.t_ritz = now_s() - t_r0; P.t_total = now_s() - t_begin;
+}
+
+// ---------------------------------------------------------------- diagnostics: the dense kernels of the Lanczos phase alone
+// One CGS pass (c = V^T z, z -= Z c) over k basis columns, the Ritz product U = V S (k x ns) and the Gram block
+// U^T W (ns x ns) on random data of local length n: microseconds per call (CUDA events, 3 repetitions after one
+// warm-up).  Used by tools/lanczos_kernels.py for the live numbers and as the ncu target of K6/K7.
+extern "C" int nm_diag_lanczos_kernels(long long n_, int k, int ns, double* us_out /* 4: gemvT+reduce, gemvN, ritz, gram */) {
+  NM_API_BEGIN
+  nm_ensure_init();
+  NmCtx& ctx = nm_ctx();
+  const size_t n = (size_t)n_;
+  NM_REQUIRE(n > 0 && k > 0 && ns > 0, "nm_diag_lanczos_kernels: bad sizes");
+  Basis V;
+  V.init(n);
+  for (int j = 0; j < k; ++j) nm_vec_random(V.col(j), n, 99, (unsigned long long)j * n);
+  DBuf<double> z(n), cbuf(k + 1), U((size_t)ns * n), S((size_t)k * ns), G((size_t)ns * ns);
+  nm_vec_random(z.p, n, 7, 0);
+  nm_vec_random(S.p, (size_t)k * ns, 8, 0);
+  const int ntiles = nm_div_up((long long)n, GT_ROWS);
+  cudaEvent_t e0, e1;
+  NM_CUDA(cudaEventCreate(&e0)); NM_CUDA(cudaEventCreate(&e1));
+  auto timed = [&](int which) {
+    for (int rep = -1; rep < 3; ++rep) {
+      if (rep == 0) NM_CUDA(cudaEventRecord(e0, ctx.stream));
+      if (which == 0) {
+        for (int j0 = 0; j0 < k; j0 += V.cpc) {
+          const int nc = std::min(V.cpc, k - j0);
+          double* partial = nm_red_scratch((size_t)V.cpc * ntiles);
+          dim3 grid(ntiles, nm_div_up(nc, GT_COLS));
+          k_gemvT<<<grid, GT_THREADS, 0, ctx.stream>>>(V.col(j0), n, nc, z.p, partial, ntiles);
+          k_reduce_partials<<<nm_div_up(nc, 8), 256, 0, ctx.stream>>>(partial, ntiles, nc, cbuf.p + j0);
+        }
+      } else if (which == 1) {
+        for (int j0 = 0; j0 < k; j0 += V.cpc) {
+          const int nc = std::min(V.cpc, k - j0);
+          k_gemvN<<<nm_div_up((long long)n, 256), 256, nc * sizeof(double), ctx.stream>>>(V.col(j0), n, nc, cbuf.p + j0, z.p);
+        }
+      } else if (which == 2) {
+        ritz_vectors(V, k, S.p, k, ns, U.p);
+      } else {
+        gram(U.p, U.p, n, ns, ns, G.p);
+      }
+    }
+    NM_CUDA(cudaEventRecord(e1, ctx.stream));
+    NM_CUDA(cudaStreamSynchronize(ctx.stream));
+    float ms;
+    NM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    return (double)ms * 1e3 / 3.0;
+  };
+  for (int w = 0; w < 4; ++w) us_out[w] = timed(w);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  NM_API_END
 }
 
 // ---------------------------------------------------------------- C ABI: solver context

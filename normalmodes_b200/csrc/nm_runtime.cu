@@ -1,6 +1,7 @@
 // Runtime context, error reporting, NCCL plumbing and the small vector kernels of the
 // Lanczos driver (axpy / dot / scale).  All work is queued on one stream (nm_ctx().stream).
 #include "nm_internal.h"
+#include <algorithm>
 #include <cstdarg>
 #include <mutex>
 
@@ -168,14 +169,48 @@ static void p2p_setup() {
   c.dev_status = (int*)(c.push_ctr + 32);
 }
 
+// Window slots: first-fit from the free list of released slots, else bump allocation; a slot is zeroed before it is
+// handed out (arrival flags and flag-in-data tags of its previous owner must not satisfy a new matrix' first wait).
+// Allocation order is collective (every rank creates / frees the same matrices in the same order), and the offsets
+// are exchanged through the communicator afterwards, which also orders the zeroing before any peer's first store.
+static std::vector<std::pair<size_t, size_t>> g_win_free;       // (offset, bytes), 256-byte granules
 size_t nm_win_alloc(size_t bytes) {
   NmCtx& c = g_ctx;
   NM_REQUIRE(c.p2p, "nm_win_alloc without a peer window");
-  const size_t off = (c.win_used + 255) & ~(size_t)255;
-  NM_REQUIRE(off + bytes <= c.win_bytes, "peer window exhausted (%zu + %zu > %zu bytes): raise NM_P2P_WINDOW_MB", off, bytes,
-             c.win_bytes);
-  c.win_used = off + bytes;
+  bytes = (bytes + 255) & ~(size_t)255;
+  size_t off = (size_t)-1;
+  for (size_t i = 0; i < g_win_free.size(); ++i)
+    if (g_win_free[i].second >= bytes) {
+      off = g_win_free[i].first;
+      if (g_win_free[i].second == bytes) g_win_free.erase(g_win_free.begin() + i);
+      else { g_win_free[i].first += bytes; g_win_free[i].second -= bytes; }
+      break;
+    }
+  if (off == (size_t)-1) {
+    off = (c.win_used + 255) & ~(size_t)255;
+    NM_REQUIRE(off + bytes <= c.win_bytes, "peer window exhausted (%zu + %zu > %zu bytes): raise NM_P2P_WINDOW_MB", off, bytes,
+               c.win_bytes);
+    c.win_used = off + bytes;
+  }
+  NM_CUDA(cudaMemsetAsync(c.win + off, 0, bytes, c.stream));
   return off;
+}
+void nm_win_free(size_t off, size_t bytes) {
+  NmCtx& c = g_ctx;
+  if (!c.p2p || !c.win) return;
+  bytes = (bytes + 255) & ~(size_t)255;
+  g_win_free.emplace_back(off, bytes);
+  // merge neighbours so that a sequence of create / free of the same matrices does not fragment the window
+  std::sort(g_win_free.begin(), g_win_free.end());
+  for (size_t i = 0; i + 1 < g_win_free.size();)
+    if (g_win_free[i].first + g_win_free[i].second == g_win_free[i + 1].first) {
+      g_win_free[i].second += g_win_free[i + 1].second;
+      g_win_free.erase(g_win_free.begin() + i + 1);
+    } else ++i;
+  if (!g_win_free.empty() && g_win_free.back().first + g_win_free.back().second == c.win_used) {
+    c.win_used = g_win_free.back().first;
+    g_win_free.pop_back();
+  }
 }
 
 void nm_check_device_status() {
@@ -213,6 +248,7 @@ extern "C" int nm_comm_finalize(void) {
       g_ctx.peer_win.clear();
       cudaFree(g_ctx.win); cudaFree(g_ctx.push_ctr);
       g_ctx.win = nullptr; g_ctx.push_ctr = nullptr; g_ctx.dev_status = nullptr; g_ctx.p2p = false;
+      g_win_free.clear(); g_ctx.win_used = 0;
     }
     ncclCommDestroy(g_ctx.nccl);
     g_ctx.nccl = nullptr;

@@ -29,6 +29,8 @@ struct NmSlabHost {
   int nchunk = 0, grid = 0, threads = 0, max_chunks_per_cta = 0, stage_bytes = 0, xs_doubles = 0, nstage = 0, smem_bytes = 0;
   int ws = 0, nxs = 2, nprod = 0;
   long long padded_entries = 0;
+  std::vector<int> desc_cid;               // chunk id (pack-order index) of every descriptor (the CTA ranges are reordered)
+  bool deps_ok = false;                    // every blob carries the ids of the chunks that own its columns, symmetric
 };
 
 // rp/idx: row pointers and column ids (< ncolb) of the n index rows; R scalar rows/columns per index entry;
@@ -175,9 +177,37 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
   std::vector<int> newid(n);
   for (int i = 0; i < n; ++i) newid[final_order[i]] = i;
   auto colid = [&](int c) { return c < n ? newid[c] : c; };                  // ghosts (>= n) keep their id
+  // ---- 2b. chunk dependencies (dataflow execution of the persistent kernel): the chunks that own the columns a chunk
+  // gathers.  A Chebyshev step of chunk c may start as soon as THOSE chunks have finished the previous step; for a
+  // symmetric pattern the relation is symmetric, which is what makes the two alternating direction buffers safe
+  // without a grid barrier (a chunk cannot overwrite values a neighbour still has to gather).
+  const int nchunk = (int)chunks.size();
+  std::vector<std::vector<int>> deps(nchunk);
+  {
+    std::vector<int> chunk_of(n);
+    for (int i = 0; i < nchunk; ++i)
+      for (int j = 0; j < chunks[i].nr; ++j) chunk_of[chunks[i].first + j] = i;
+    std::vector<int> mark(nchunk, -1);
+    for (int i = 0; i < nchunk; ++i) {
+      for (int j = 0; j < chunks[i].nr; ++j) {
+        const int row = final_order[chunks[i].first + j];
+        for (int p = rp[row]; p < rp[row + 1]; ++p) {
+          if (idx[p] >= n) continue;                                        // ghost column: flag-in-data slot
+          const int c2 = chunk_of[newid[idx[p]]];
+          if (mark[c2] != i) { mark[c2] = i; deps[i].push_back(c2); }
+        }
+      }
+      std::sort(deps[i].begin(), deps[i].end());
+    }
+    bool sym = true;
+    for (int i = 0; i < nchunk && sym; ++i)
+      for (int c2 : deps[i])
+        if (!std::binary_search(deps[c2].begin(), deps[c2].end(), i)) { sym = false; break; }
+    H.deps_ok = sym && nm_env_int("NM_SLAB_DEPS", 1) != 0;
+    if (!H.deps_ok) for (auto& d : deps) d.clear();
+  }
   // ---- 3. blobs.  Lane t of a chunk walks one share of a row; slice s = lanes 32s..32s+31 (one warp), padded
   // to its longest lane.
-  const int nchunk = (int)chunks.size();
   std::vector<NmPackDesc> desc(nchunk);
   std::vector<size_t> start(nchunk);
   std::vector<int> nep_of(nchunk);
@@ -195,7 +225,8 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
       nep += 32 * w;
     }
     nep_of[i] = nep;
-    size_t b = 32 + up16(8 * (size_t)c.nslice) + 8 * (size_t)nep + 4 * (size_t)c.nd + 2 * (size_t)nep + 2 * (size_t)(32 * c.nslice);
+    size_t b = 32 + up16(8 * (size_t)c.nslice) + 8 * (size_t)nep + 4 * (size_t)c.nd + 2 * (size_t)nep + 2 * (size_t)(32 * c.nslice) +
+               4 * deps[i].size();
     b = up16(b);
     start[i] = total;
     desc[i].off16 = (unsigned)(total / 16);
@@ -233,7 +264,7 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
       for (int p = rp[rows[j]]; p < rp[rows[j] + 1]; ++p)
         if (idx[p] >= n) { has_ghost = 1; break; }
     ghost_chunk[i] = (char)has_ghost;
-    NmSlabHeader h{c.nr, c.nd, nslice, c.first, nep, gmax, has_ghost, 0};
+    NmSlabHeader h{c.nr, c.nd, nslice, c.first, nep, gmax, has_ghost, (int)deps[i].size()};
     memcpy(base, &h, sizeof(h));
     const size_t o_tbl = 32;
     const size_t o_val = 32 + up16(8 * (size_t)nslice);
@@ -244,6 +275,7 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
     int* bcols = (int*)(base + o_cols);
     unsigned short* bidx = (unsigned short*)(base + o_idx);
     unsigned short* blane = (unsigned short*)(base + o_lane);
+    if (!deps[i].empty()) memcpy(base + o_lane + 2 * (size_t)(32 * nslice), deps[i].data(), 4 * deps[i].size());
     // per-lane word of the kernel: bit 15 = first lane of its row (does the epilogue), bits 10..14 = steps s of
     // the shuffle tree at which lane + 2^s belongs to the same row (add its partial), bits 0..9 = local row
     for (int t = 0; t < 32 * nslice; ++t) {
@@ -487,11 +519,18 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
   // processing order inside a CTA's range: chunks without ghost columns first, so that on several GPUs the chunks
   // that need the peers' values come last and the halo exchange overlaps the interior ones (the row positions are in
   // the blob headers: the order of the descriptors is free)
+  H.desc_cid.resize(nchunk);
   for (int g = 0; g < grid; ++g) {
     std::vector<NmPackDesc> in, bd;
-    for (int ci = H.cta_first[g]; ci < H.cta_first[g + 1]; ++ci) (ghost_chunk[ci] ? bd : in).push_back(desc[ci]);
+    std::vector<int> in_id, bd_id;
+    for (int ci = H.cta_first[g]; ci < H.cta_first[g + 1]; ++ci) {
+      (ghost_chunk[ci] ? bd : in).push_back(desc[ci]);
+      (ghost_chunk[ci] ? bd_id : in_id).push_back(ci);
+    }
     std::copy(in.begin(), in.end(), desc.begin() + H.cta_first[g]);
     std::copy(bd.begin(), bd.end(), desc.begin() + H.cta_first[g] + in.size());
+    std::copy(in_id.begin(), in_id.end(), H.desc_cid.begin() + H.cta_first[g]);
+    std::copy(bd_id.begin(), bd_id.end(), H.desc_cid.begin() + H.cta_first[g] + in_id.size());
   }
   H.grid = grid;
   H.padded_entries = pentries;
@@ -521,6 +560,9 @@ void nm_slab_build_into(NmParcsr& M, NmSlab& S, const std::vector<int>& rp, cons
   S.slot_off8.from_host(H.slot_off8);
   S.slot_src.from_host(H.slot_src);
   S.order.from_host(H.order);
+  S.desc_cid.from_host(H.desc_cid);
+  S.deps_ok = H.deps_ok;
+  S.cflag.alloc(H.nchunk); S.cflag.zero();
   S.nchunk = H.nchunk;
   if (nm_env_int("NM_SLAB_TRACE", 0)) { S.trace.alloc((size_t)S.grid * NM_SLAB_MAXDESC * 8); S.trace.zero(); }
   nm_slab_fill_from(M, S);
@@ -566,7 +608,12 @@ extern "C" int nm_slab_host_selftest(int n, int ncolb, int R, const int* rp_, co
         xs[j] = x[(size_t)R * orig + (j - R * node)];
       }
       const unsigned short* slane = sidx + h.nep;
-      NM_REQUIRE((const unsigned char*)(slane + 32 * h.nslice) <= st + H.desc[ci].bytes, "slab: blob overrun (lanes)");
+      NM_REQUIRE((const unsigned char*)(slane + 32 * h.nslice) + 4 * (size_t)h.pad2 <= st + H.desc[ci].bytes, "slab: blob overrun (lanes / deps)");
+      {
+        const int* dp = (const int*)(slane + 32 * h.nslice);
+        for (int q = 0; q < h.pad2; ++q) NM_REQUIRE(dp[q] >= 0 && dp[q] < H.nchunk, "slab: dependency id");
+        NM_REQUIRE(H.desc_cid[ci] >= 0 && H.desc_cid[ci] < H.nchunk, "slab: chunk id");
+      }
       int owners = 0;
       for (int warp = 0; warp < H.threads / 32; ++warp) {
         double acc[32][3];

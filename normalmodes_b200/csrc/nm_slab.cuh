@@ -42,18 +42,20 @@ struct NmSlabView {
   const int* scols;
   const unsigned short* sidx;
   const unsigned short* slane;   // per lane: bit 15 first lane of its row, bits 10..14 shuffle-tree adds, bits 0..9 local row
+  const int* deps;               // h.pad2 chunk ids: the owners of the chunk's (non-ghost) columns
 };
 __device__ __forceinline__ NmSlabView nm_slab_view(const unsigned char* st) {
   NmSlabView v;
   const int4 a = *(const int4*)st;
   const int4 b = *(const int4*)(st + 16);
   v.h.nr = a.x; v.h.nd = a.y; v.h.nslice = a.z; v.h.first = a.w; v.h.nep = b.x; v.h.gmax = b.y;
-  v.h.has_ghost = b.z; v.h.pad2 = 0;
+  v.h.has_ghost = b.z; v.h.pad2 = b.w;
   v.tbl = (const uint2*)(st + 32);
   v.sv = (const double*)(st + 32 + ((8 * v.h.nslice + 15) & ~15));
   v.scols = (const int*)(v.sv + v.h.nep);
   v.sidx = (const unsigned short*)(v.scols + v.h.nd);
   v.slane = v.sidx + v.h.nep;
+  v.deps = (const int*)(v.slane + 32 * v.h.nslice);
   return v;
 }
 
@@ -223,19 +225,22 @@ struct NmSlabWsArgs {
   int ghost_cg;             // 1: read ghost values with ld.global.cg (synchronous); 0: cp.async like the owned ones
 };
 
-// Fused multi-GPU step (NM_HALO_FUSED=1, off by default -- written after the round's last GPU run, to be validated
-// first thing next round): no kernel between two steps.  The first lane of a boundary row stores its new direction
-// straight into the peers' ghost buffers (NVLink peer window) from the epilogue; every consumer warp fences its peer
-// stores and counts itself done; the grid's last warp raises this rank's arrival flag in every destination window.
-// The next step polls the flags before its first chunk with ghost columns, as in the overlapped exchange.
+// Fused multi-GPU step (default on several GPUs): no kernel, fence, flag or atomic between two steps.  The first lane of a
+// boundary row stores its new direction straight into the peers' flag-in-data ghost slots (nm_ll_store: NVLink peer
+// window, 16 bytes per value, tag = epoch of the step) from the epilogue; the next step's producers poll the slots they
+// gather (nm_ll_load) before the chunks that have ghost columns, which come last in every CTA's range -- the values were
+// sent a whole step earlier.  Three rotating slot buffers: the kernel boundary keeps a GPU's CTAs within one step,
+// and a peer can only enter step k+2 after ALL of this rank's step k+1 (it gathers from it).  Measured against the
+// round-1 scheme (peer stores + system fences + arrival flags: two serialised fence.sys round trips and a flag flight
+// per step): 200k-tet bench workload on 2 GPUs 14.5 s -> 9.8 s per filter application (profiles/r2*).
 struct NmSlabFusedArgs {
   const int* push_off;          // per pack-order index row: [off, off') into push_ent; null = nothing to push
   const NmPushEnt* push_ent;    // peer, scalar component, position in that peer's ghost buffer
-  double* peer_xg[8];           // this rank's block in each peer's ghost buffer (parity of push_epoch applied)
-  unsigned long long* peer_flag[8];
-  unsigned send_mask;
-  unsigned long long push_epoch;
-  unsigned* ctr;                // consumer warps done (device counter, reset by the last one)
+  unsigned long long* ll_out[8];        // this rank's block of slots in each peer's buffer of tag_out
+  const unsigned long long* ll_in;      // this rank's ghost slots of tag_in (null: no ghosts gathered through slots)
+  unsigned tag_in, tag_out;
+  int* status;
+  int debug;                    // NM_DEBUG_LL bit 0: no tag wait (timing diagnostics only)
 };
 
 // ghost values were written by a peer GPU during this kernel's lifetime: read them through L2 (no L1 allocation)
@@ -253,6 +258,54 @@ __device__ __forceinline__ void nm_slab_gather_ghost(const NmSlabView& v, double
     const int c = R * v.scols[node] + (j - R * node);
     if (c < ncol) nm_cp_async8(xs + j, x + c);
     else xs[j] = nm_ld_cg(xg + (c - ncol));
+  }
+  __threadfence_block();                                         // the plain stores above precede the barrier arrival
+}
+
+template <int R>
+__device__ __forceinline__ void nm_slab_gather_ll(const NmSlabView& v, double* xs, const double* __restrict__ x,
+                                                  const unsigned long long* ll, unsigned tag, int* status, int ncol,
+                                                  int t, int nthreads, bool nowait = false) {
+  const int tot = R * v.h.nd;
+  // 4 independent column ids / slot loads in flight per thread: a ghost value is a dependent 16-byte L2 load, and a
+  // boundary chunk has hundreds of them.  NM_DEBUG_LL (diagnostics, bit 0): do not wait for the tags (timing of the
+  // kernel without the exchange latency; results are then wrong)
+  for (int j = t; j < tot; j += 4 * nthreads) {
+    int cc[4];
+    unsigned a[4], fa[4], b[4], fb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int jj = j + u * nthreads;
+      cc[u] = -1;
+      if (jj < tot) {
+        const int node = (R == 1) ? jj : jj / 3;
+        cc[u] = R * v.scols[node] + (jj - R * node);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int jj = j + u * nthreads;
+      fa[u] = fb[u] = tag; a[u] = b[u] = 0u;
+      if (cc[u] < 0) continue;
+      if (cc[u] < ncol) { nm_cp_async8(xs + jj, x + cc[u]); continue; }
+      asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(a[u]), "=r"(fa[u]), "=r"(b[u]), "=r"(fb[u]) : "l"(ll + 2 * (size_t)(cc[u] - ncol)) : "memory");
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (cc[u] < ncol) continue;                                // nothing (-1) or an owned column (cp.async above)
+      double val = __longlong_as_double((long long)(((unsigned long long)b[u] << 32) | a[u]));
+      if ((fa[u] != tag || fb[u] != tag) && !nowait) {
+        val = 0.0;
+        const unsigned long long* slot = ll + 2 * (size_t)(cc[u] - ncol);
+        const long long t0 = clock64();
+        while (!nm_ll_load(slot, tag, &val)) {
+          if (*(volatile int*)status != 0) break;                                  // an earlier wait already failed
+          if (clock64() - t0 > 20000000000ll) { atomicOr(status, 1); break; }      // ~10 s: peer stalled or died
+        }
+      }
+      xs[j + u * nthreads] = val;
+    }
   }
   __threadfence_block();                                         // the plain stores above precede the barrier arrival
 }
@@ -312,7 +365,9 @@ __global__ void __launch_bounds__(32 * (NC + 8)) k_slabws(NmSlabWsArgs W, Epi ep
       if (it >= X) nm_mbar_wait_bounded(empty_xs + xb, (uint32_t)(((it / X) - 1) & 1));
       const NmSlabView v = nm_slab_view(stage0 + (size_t)s * A.stage_bytes);
       double* xs = xs0 + (size_t)xb * A.xs_doubles;
-      if (v.h.has_ghost && W.hmask) {
+      if (FUSED && v.h.has_ghost && F.ll_in) {
+        nm_slab_gather_ll<R>(v, xs, x, F.ll_in, F.tag_in, F.status, ncol, ptid, pthreads, (F.debug & 1) != 0);
+      } else if (v.h.has_ghost && W.hmask) {
         if (!flags_seen) {
           if (lane == 0) {
             for (int r = 0; r < 8; ++r) {
@@ -408,28 +463,12 @@ __global__ void __launch_bounds__(32 * (NC + 8)) k_slabws(NmSlabWsArgs W, Epi ep
             double val = dn[0];
 #pragma unroll
             for (int c = 1; c < R; ++c) if (pe.comp == c) val = dn[c];
-            F.peer_xg[pe.peer][pe.dst] = val;
+            nm_ll_store(F.ll_out[pe.peer] + 2 * (size_t)pe.dst, val, F.tag_out);
           }
         }
       } else {
 #pragma unroll
         for (int c = 0; c < R; ++c) epi.apply(row0 + c, acc[c], in[c]);
-      }
-    }
-  }
-  if constexpr (FUSED) {
-    if (F.push_off) {
-      __syncwarp();                                               // the warp's peer stores happen-before lane 0's fence
-      if (lane == 0) {
-        __threadfence_system();
-        const unsigned total = gridDim.x * NC;
-        if (atomicAdd(F.ctr, 1u) == total - 1) {                  // last consumer warp of the grid: every store is ordered
-          __threadfence_system();
-          for (int r = 0; r < 8; ++r)
-            if (F.send_mask & (1u << r))
-              asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(F.peer_flag[r]), "l"(F.push_epoch) : "memory");
-          *F.ctr = 0;
-        }
       }
     }
   }
@@ -462,6 +501,9 @@ struct NmSlabPersArgs {
   double inv_theta;
   unsigned long long* gbar; // grid-barrier counter (monotonic over the solves of this ChebIter)
   unsigned long long gbase; // its value when this launch starts
+  // dataflow execution (null: grid barrier per step instead): per-chunk completion flags, chunk id per descriptor
+  unsigned* cflag; const int* desc_cid;
+  unsigned ftag0;           // a chunk that has finished step k carries ftag0 + k + 1
   // several GPUs (null / 0 on one)
   const unsigned long long* ll_in[3];   // this rank's ghost slots, by tag % 3
   unsigned long long* ll_out[3][8];     // this rank's block of slots in each peer's buffers
@@ -470,47 +512,31 @@ struct NmSlabPersArgs {
   int* hstatus;
 };
 
-template <int R>
-__device__ __forceinline__ void nm_slab_gather_ll(const NmSlabView& v, double* xs, const double* __restrict__ x,
-                                                  const unsigned long long* ll, unsigned tag, int* status, int ncol,
-                                                  int t, int nthreads) {
-  const int tot = R * v.h.nd;
-  for (int j = t; j < tot; j += nthreads) {
-    const int node = (R == 1) ? j : j / 3;
-    const int c = R * v.scols[node] + (j - R * node);
-    if (c < ncol) { nm_cp_async8(xs + j, x + c); continue; }
-    double val = 0.0;
-    const unsigned long long* slot = ll + 2 * (size_t)(c - ncol);
-    const long long t0 = clock64();
-    while (!nm_ll_load(slot, tag, &val)) {
-      if (*(volatile int*)status != 0) break;                                    // an earlier wait already failed
-      if (clock64() - t0 > 20000000000ll) { atomicOr(status, 1); break; }        // ~10 s: peer stalled or died
-    }
-    xs[j] = val;
-  }
-  __threadfence_block();                                         // the plain stores above precede the barrier arrival
-}
-
+// shared memory in front of the x buffers: descriptors, chunk ids, 5 x 8 mbarriers
+#define NM_SLABPERS_FIXED (NM_SLAB_MAXDESC * (sizeof(NmPackDesc) + sizeof(int)) + 384)
 template <int R, int NC>
-__global__ void __launch_bounds__(32 * (NC + 8)) k_slabpers(NmSlabPersArgs W) {
+__global__ void __launch_bounds__(32 * (NC + 9)) k_slabpers(NmSlabPersArgs W) {
   const NmSlabArgs& A = W.a;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c0 = A.cta_first[blockIdx.x];
   const int n = A.cta_first[blockIdx.x + 1] - c0;                // >= 1 for every CTA (packer)
   const int S = A.nstage, X = W.nxs, NP = W.np, deg = W.deg;
+  const bool flow = W.cflag != nullptr;                          // dataflow: per-chunk flags instead of the grid barrier
   NmPackDesc* sdesc = (NmPackDesc*)smem;
-  uint64_t* full_blob = (uint64_t*)(smem + NM_SLAB_MAXDESC * sizeof(NmPackDesc));
+  int* scid = (int*)(smem + NM_SLAB_MAXDESC * sizeof(NmPackDesc));
+  uint64_t* full_blob = (uint64_t*)(smem + NM_SLAB_MAXDESC * (sizeof(NmPackDesc) + sizeof(int)));
   uint64_t* empty_blob = full_blob + 8;
   uint64_t* full_xs = full_blob + 16;
   uint64_t* empty_xs = full_blob + 24;
-  double* xs0 = (double*)(full_blob + 32);
-  unsigned char* stage0 =
-      smem + ((NM_SLAB_MAXDESC * sizeof(NmPackDesc) + 256 + 8 * (size_t)X * A.xs_doubles + 15) & ~(size_t)15);
-  for (int i = tid; i < n; i += blockDim.x) sdesc[i] = A.desc[c0 + i];
+  uint64_t* done_xs = full_blob + 32;                            // dataflow: all consumer warps have STORED a visit's rows
+  double* xs0 = (double*)(full_blob + 48);
+  unsigned char* stage0 = smem + ((NM_SLABPERS_FIXED + 8 * (size_t)X * A.xs_doubles + 15) & ~(size_t)15);
+  for (int i = tid; i < n; i += blockDim.x) { sdesc[i] = A.desc[c0 + i]; if (flow) scid[i] = W.desc_cid[c0 + i]; }
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { nm_mbar_init(full_blob + s, 1); nm_mbar_init(empty_blob + s, NC); }
-    for (int x = 0; x < X; ++x) { nm_mbar_init(full_xs + x, 32 * NP); nm_mbar_init(empty_xs + x, NC); }
+    // dataflow: an x buffer is reused only after the publisher warp has raised the visit's flag as well
+    for (int x = 0; x < X; ++x) { nm_mbar_init(full_xs + x, 32 * NP); nm_mbar_init(empty_xs + x, flow ? NC + 1 : NC); nm_mbar_init(done_xs + x, NC); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -518,6 +544,22 @@ __global__ void __launch_bounds__(32 * (NC + 8)) k_slabpers(NmSlabPersArgs W) {
   // q = k (n - P) + (it - P) over the whole solve
   const int P = n <= S ? n : S - 2, RG = n <= S ? 0 : 2, NR = n - P;
   const bool multi = W.push_off != nullptr;
+  if (warp >= NC + NP) {
+    // ================================================= publisher (dataflow only): one thread
+    // When every consumer warp has stored its rows of a visit (done_xs), ONE gpu-scope release makes them visible and
+    // raises the chunk's flag; only then may the visit's x buffer be reused, so the publisher is never lapped.
+    if (!flow || lane != 0) return;
+    for (int k = 0; k < deg; ++k)
+      for (int it = 0; it < n; ++it) {
+        const long long gx = (long long)k * n + it;
+        const int xb = (int)(gx % X);
+        nm_mbar_wait_bounded(done_xs + xb, (uint32_t)((gx / X) & 1));
+        if (k < deg - 1)
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(W.cflag + scid[it]), "r"(W.ftag0 + (unsigned)k + 1u) : "memory");
+        nm_mbar_arrive(empty_xs + xb);
+      }
+    return;
+  }
   if (warp >= NC) {
     // ================================================= producers
     const int pw = warp - NC;
@@ -558,7 +600,7 @@ __global__ void __launch_bounds__(32 * (NC + 8)) k_slabpers(NmSlabPersArgs W) {
     const int ncol = A.ncol;
     for (int k = 0; k < deg; ++k) {
       const double* __restrict__ x = k == 0 ? W.b : ((k & 1) ? W.d0 : W.d1);      // direction written by step k-1
-      if (k > 0) {
+      if (k > 0 && !flow) {
         // grid barrier: every CTA has stored (and fenced) its step k-1 directions
         if (ptid == 0) {
           const unsigned long long target = W.gbase + (unsigned long long)k * gridDim.x;
@@ -586,8 +628,25 @@ __global__ void __launch_bounds__(32 * (NC + 8)) k_slabpers(NmSlabPersArgs W) {
           if (ptid == 0) pump(q);
         }
         nm_mbar_wait_bounded(full_blob + s, par);
-        if (gx >= X) nm_mbar_wait_bounded(empty_xs + xb, (uint32_t)(((gx / X) - 1) & 1));
         const NmSlabView v = nm_slab_view(stage0 + (size_t)s * A.stage_bytes);
+        if (flow && k > 0) {
+          // dataflow: the chunks owning this chunk's columns have finished step k-1 (relaxed polls, one acquire fence --
+          // which also drops the SM's stale L1 lines of the alternating d buffers -- then the producers' barrier)
+          const unsigned target = W.ftag0 + (unsigned)k;
+          for (int j = ptid; j < v.h.pad2; j += pthreads) {
+            const unsigned* f = W.cflag + v.deps[j];
+            unsigned fv;
+            const long long t0 = clock64();
+            for (;;) {
+              asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(fv) : "l"(f) : "memory");
+              if ((int)(fv - target) >= 0) break;
+              if (clock64() - t0 > 60000000000ll) __trap();                       // ~30 s: never hang the GPU
+            }
+          }
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"r"(pthreads) : "memory");
+        }
+        if (gx >= X) nm_mbar_wait_bounded(empty_xs + xb, (uint32_t)(((gx / X) - 1) & 1));
         double* xs = xs0 + (size_t)xb * A.xs_doubles;
         if (multi && v.h.has_ghost) nm_slab_gather_ll<R>(v, xs, x, ll, tag, W.hstatus, ncol, ptid, pthreads);
         else nm_slab_gather<R>(v, xs, x, x, ncol, ptid, pthreads);
@@ -678,8 +737,12 @@ __global__ void __launch_bounds__(32 * (NC + 8)) k_slabpers(NmSlabPersArgs W) {
           }
         }
       }
+      if (flow) {
+        __syncwarp();                                            // the warp's stores of this visit precede lane 0's arrival
+        if (lane == 0) nm_mbar_arrive(done_xs + xb);
+      }
     }
-    if (k < deg - 1) {
+    if (k < deg - 1 && !flow) {
       // this CTA's directions of step k are stored: count it in at the grid barrier (the producers wait)
       asm volatile("bar.sync 2, %0;" ::"r"(cthreads) : "memory");
       if (tid == 0) {
@@ -700,7 +763,7 @@ static inline void nm_slabpers_launch_t(NmSlab& S, const NmSlabPersArgs& W) {
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(S.grid); cfg.blockDim = dim3(32 * (NC + S.nprod)); cfg.dynamicSmemBytes = S.pers_smem; cfg.stream = c.stream;
+  cfg.gridDim = dim3(S.grid); cfg.blockDim = dim3(32 * (NC + S.nprod + 1)); cfg.dynamicSmemBytes = S.pers_smem; cfg.stream = c.stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;                   // every CTA resident: the grid barrier cannot deadlock
   attr[0].val.cooperative = 1;

@@ -50,16 +50,22 @@ def read_model(prefix, ntet, porder, job):
 
 
 def _list_directed_real4(v):
-    """Text of `write(s,*) real(v,4)` as gfortran prints it (9 significant digits, trailing zeros kept by the 'G0'-like
-    rule are dropped); Intel Fortran prints 7 digits -- the file name is compiler-dependent in the reference too."""
+    """Text of `write(s,*) real(v,4)` as gfortran prints it (list-directed REAL(4) = 1PG16.9E2-like: 9 significant
+    digits in total; F form with 9 - (integer digits) decimals for 0.1 <= |x| < 1e9, otherwise d.ddddddddE+ee).
+    Intel Fortran prints 7 digits -- the file name is compiler-dependent in the reference too (src/mod_para.f90:271-289)."""
     x = float(np.float32(v))
-    s = "%.9g" % x
-    if "e" not in s and "." not in s:
-        s += ".00000000"
-    elif "e" not in s:
-        digits = len(s.replace("-", "").replace(".", "").lstrip("0"))
-        s += "0" * max(0, 9 - digits)
-    return s
+    if x == 0.0:
+        return "0.00000000"
+    ax = abs(x)
+    if ax < 0.1 or ax >= 1.0e9:
+        m, e = ("%.8E" % x).split("E")
+        return "%sE%s%02d" % (m, e[0], abs(int(e)))
+    e10 = int(np.floor(np.log10(ax)))
+    if float("%.9g" % ax) >= 10.0 ** (e10 + 1):             # rounding carried into the next decade (9.9999999999 -> 10.0)
+        e10 += 1
+    nint = max(e10 + 1, 0)                                  # digits in front of the decimal point (0.2 -> none counted)
+    dec = 9 - nint if nint > 0 else 9
+    return "%.*f" % (dec, x)
 
 
 def output_names(outputdir, basename, job, porder, nproc, lowfreq, upfreq):

@@ -427,7 +427,11 @@ def truth_eigs(mats, a, b, dense_limit=6000):
             w = spla.eigsh(Aop, k=min(k, n - 2), M=Bm.tocsc(), sigma=sigma, which="LM", OPinv=OPinv,
                            return_eigenvectors=False)
             w = np.sort(w)
-            if (w.min() < a and w.max() > b) or k >= n - 2:
+            # shift-invert returns the k eigenvalues NEAREST sigma: everything within rho = max|w - sigma| of it is in w.
+            # (Fluid models have a dense cluster of small eigenvalues below the band: waiting for w.max() > b as well
+            # would drag the whole cluster in.)
+            rho = np.abs(w - sigma).max()
+            if (sigma - rho <= a and sigma + rho >= b) or k >= n - 2:
                 return w[(w >= a) & (w <= b)]
             k *= 2
     A, B = effective_pencil(mats)
@@ -440,6 +444,7 @@ def truth_eigs(mats, a, b, dense_limit=6000):
     while True:
         w = spla.eigsh(A, k=min(k, n - 2), M=B, sigma=sigma, which="LM", return_eigenvectors=False)
         w = np.sort(w)
-        if (w.min() < a and w.max() > b) or k >= n - 2:
+        rho = np.abs(w - sigma).max()
+        if (sigma - rho <= a and sigma + rho >= b) or k >= n - 2:
             return w[(w >= a) & (w <= b)]
         k *= 2

@@ -27,16 +27,19 @@ def _ngpu():
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
 def test_two_ranks_halo_exchange_and_solve():
-    """Default: persistent ChebIter kernel, boundary rows stored into the peers' flag-in-data slots from the epilogue."""
+    """Default: per-step ChebIter kernels chained by dependent launch, boundary rows stored into the peers' flag-in-data
+    slots from the epilogue (no kernel, fence or flag between steps); P1 fluid-solid and P2 solid fixtures."""
     out = _run(2, 29611)
     print(out[-1500:])
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("env", [dict(NM_SLAB_PERS="0"), dict(NM_SLAB_PERS="0", NM_HALO_OVERLAP="0"), dict(NM_P2P="0")])
-def test_two_ranks_blocking_exchange_and_nccl_fallback(env):
-    """Per-step launches with the overlapped peer-window exchange (flags polled by the step kernel), the blocking
-    exchange (flags awaited in k_halo_push) and the NCCL send/recv fallback."""
+@pytest.mark.parametrize("env", [dict(NM_SLAB_PERS="1"), dict(NM_SLAB_PERS="1", NM_SLAB_FLOW="0"), dict(NM_HALO_FUSED="0"),
+                                 dict(NM_HALO_FUSED="0", NM_HALO_OVERLAP="0"), dict(NM_P2P="0")])
+def test_two_ranks_other_transports(env):
+    """The persistent kernel with the in-kernel slot exchange (dataflow flags / grid barrier), the round-1 schemes
+    (peer-window stores + arrival flags polled by the step kernel; flags awaited in k_halo_push) and the NCCL send/recv
+    fallback."""
     out = _run(2, 29615, env_extra=dict(env, NM_MP_CASES="prem3k_p1_j2"))
     print(out[-800:])
 
@@ -45,11 +48,3 @@ def test_two_ranks_blocking_exchange_and_nccl_fallback(env):
 def test_all_ranks_halo_exchange_and_solve():
     out = _run(min(_ngpu(), 8), 29613, env_extra={"NM_MP_CASES": "prem3k_p1_j2"})
     print(out[-1500:])
-
-
-@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
-def test_two_ranks_fused_step():
-    """NM_HALO_FUSED=1 (per-step launches): boundary rows stored to the peers from the step kernel's epilogue, arrival
-    flags raised by the grid's last consumer warp, no kernel between steps."""
-    out = _run(2, 29617, env_extra=dict(NM_HALO_FUSED="1", NM_SLAB_PERS="0", NM_MP_CASES="prem3k_p1_j2"))
-    print(out[-800:])

@@ -208,12 +208,13 @@ def test_solve_prem3k_fluid_solid(nm):
 
 
 def test_solve_tight_inner_degree_meets_plain_residual(nm):
-    """'tight' mode: inner degree 36 + Lanczos tol 1e-11 + per-pair Ritz gate.  The reference's own
-    acceptance figure (RMS 'relative err.', src/mod_pevsl.f90:144-162) stays <= 2e-11 for EVERY pair (median <= 1e-13);
-    the plain ||A y - lam B y||_2/|lam| has median <= 1e-12, 90% of the pairs <= 2e-11 and the worst <= 1e-9: members of
-    near-degenerate multiplets (2l+1 modes of the sphere) converge last in a single-vector Lanczos, and any fp64
-    vector carries eps*lambda_max/lambda of rounding in that norm, so the worst few pairs move by a factor of a few
-    with the summation order of the kernels (observed 6e-11 ... 1.3e-10)."""
+    """north_star residual gate: every pair's plain ||A y - lam B y||_2 / |lam| <= 1e-12 on the demo configuration
+    (src/mod_pevsl.f90:144-162 computes the RMS-normalised version of it; README.md:58 "typically around 1e-13").
+    'tight' mode: inner degree 36 (the degree-25 B-solve of the reference is only accurate to ~1e-9, which
+    the residual against the true B~ shows directly) + Lanczos tol 1e-11 + per-pair Ritz gate.  What a non-restarted
+    Lanczos stopped by the trace test leaves in a Ritz vector is mostly a mixture of OTHER wanted eigenvectors
+    (multiplet members resolve last: 5.7e-12 worst in the oracle, 6e-11..1.3e-10 on the GPU before round 2); the
+    Rayleigh-Ritz step on the accepted span (nm_cheblannr, DMMA Gram + rotation) removes exactly that."""
     from normalmodes_b200 import matvec as mv, pevsl
     c = load_case("const3k_p1_j1")
     m = mv.setupmatvec(to_coomat(c["mats"]), 1, degB=36)
@@ -225,8 +226,81 @@ def test_solve_tight_inner_degree_meets_plain_residual(nm):
     rms = pevsl.finalize_eigerr(r, m.Gpbsiz)
     print("tight mode: steps %d, plain residual/|lam| median %.2e, worst %s; RMS worst %.2e" % (
         r.steps, np.median(rel), rel[-4:], rms.max()))
-    assert np.median(rel) <= 1e-12 and np.percentile(rel, 90) <= 2e-11 and rel.max() <= 1e-9
-    assert rms.max() <= 2e-11 and np.median(rms) <= 1e-13
+    assert rel.max() <= 1e-12 and np.median(rel) <= 1e-13
+    assert rms.max() <= 1e-13
+    # the residual the library reports (from the rotated A U, B U) is the one recomputed through the operators
+    y = r.eigvec[r.nev // 2]; lam = r.eigval[r.nev // 2]
+    chk = np.linalg.norm(mv.sparseAV(y, m) - lam * mv.sparseBV(y, m))
+    assert abs(chk - r.res2[r.nev // 2]) <= 0.5 * chk + 1e-18
+
+
+def test_ritz_refinement_off_reproduces_round1(nm, monkeypatch):
+    """NM_RITZ_REFINE=0: pEVSL's plain Ritz extraction (no Rayleigh-Ritz step); same eigenvalues to 1e-10."""
+    from normalmodes_b200 import matvec as mv, pevsl
+    monkeypatch.setenv("NM_RITZ_REFINE", "0")
+    c = load_case("const3k_p1_j1")
+    m = mv.setupmatvec(to_coomat(c["mats"]), 1)
+    r = pevsl.pnm_apply_pevsl(m, 0.2, 0.8)
+    truth = np.array(c["g"]["truth_eigs"]); truth = truth[(truth >= r.xintv[0]) & (truth <= r.xintv[1])]
+    assert r.nev == len(truth) and np.max(np.abs(r.eigval - truth) / truth) < 1e-10
+
+
+def _truncated(pol, k):
+    """oracle polynomial dict cut after k degree steps (what nm_pevsl_filter_steps_host computes)."""
+    q = dict(pol); q["deg"] = k; q["mu"] = pol["mu"][:k + 1]
+    return q
+
+
+@pytest.mark.parametrize("name,ksteps", [("prem3k_p2_j2", 12), ("mtopo100k_p1_j1", 12)])
+def test_fluid_solid_operator_and_filter_on_bench_like_configs(nm, name, ksteps):
+    """The configuration bench.py times -- pOrder 2, JOB 2, fluid-solid (degB 45, degAp 100) -- on the PREM3k demo, and
+    the reference's largest demo mesh (Mtopo100k, P1): sparsefsAV, the Chebyshev B- and Ap-solves and the first degree
+    steps of one filter application against the oracle."""
+    from oracle import solver
+    from normalmodes_b200 import matvec as mv, pevsl
+    from normalmodes_b200._lib import check, dptr
+    c = load_case(name)
+    g = c["g"]
+    po = g["porder"]
+    m = mv.setupmatvec(to_coomat(c["mats"]), po)
+    assert (m.degB, m.degAp) == ((45, 100) if po == 2 else (25, 25))
+    ops = solver.Operators(c["mats"], po, bounds=dict(B=m.boundsB, Ap=m.boundsAp))
+    rng = np.random.default_rng(21)
+    v = rng.standard_normal(ops.n)
+    ref = ops.amv(v)
+    assert np.abs(mv.sparseAV(v, m) - ref).max() <= 1e-12 * np.abs(ref).max()
+    xs = mv.solveBV(v, m)
+    assert np.abs(xs - ops.bsol(v)).max() <= 1e-13 * np.abs(xs).max()
+    vp = rng.standard_normal(ops.Apt.shape[0])
+    xr = solver.chebiter(ops.Apt, m.boundsAp[0], m.boundsAp[1], m.degAp, vp)
+    assert np.abs(mv.chebiter_solve(m.chebAp, vp) - xr).max() <= 1e-13 * np.abs(xr).max()
+    # first degree steps of the filter of the case's band
+    P = mv.Pevsl(m.Gpbsiz, m.pbsiz, 0)
+    P.setbmv_op(m.opB); P.setbsol_chebiter(m.chebB); P.setamv_op(m.opA); P.set_geneig()
+    LMIN, LMAX = P.lanbounds(3000, 5000, 1.0e-5)
+    a, b = pevsl.freq_interval(g["lowfreq"], g["upfreq"], LMIN)
+    xintv = [a, b, LMIN, LMAX]
+    pol = pevsl.Pol(xintv, 0.8, 0.7)
+    ref_pol = solver.findpol(xintv, 0.8, 0.7)
+    assert pol.deg == ref_pol["deg"] and np.abs(pol.mu - ref_pol["mu"]).max() <= 1e-13
+    z = rng.standard_normal(ops.n); y = np.empty_like(z)
+    check(nm.nm_pevsl_filter_steps_host(P.h, pol.h, ksteps, dptr(z), dptr(y)))
+    yr = solver.chebav(_truncated(ref_pol, ksteps), z, ops)
+    assert np.abs(y - yr).max() <= 1e-10 * np.abs(yr).max()
+    P.finish()
+
+
+@pytest.mark.parametrize("name", ["prem3k_p2_j2", "const3k_p2_j1", "mtopo100k_p1_j1"])
+def test_solve_p2_and_large_demo_against_independent_truth(nm, name):
+    """Full solves on one GPU: P2 fluid-solid with gravity (the bench configuration, PREM3k demo), P2 solid (CONST3k)
+    and the reference's largest demo mesh (Mtopo100k, P1 fluid-solid, N = 65 241): count exact, eigenvalues 1e-10
+    against the shift-invert truth committed in tests/golden/golden.json."""
+    c, m, r = _solve(name, recheck=False)
+    truth = np.array(c["g"]["truth_eigs"])
+    truth = truth[(truth >= r.xintv[0]) & (truth <= r.xintv[1])]
+    print("%s: %d eigenpairs, %d Lanczos steps, filter degree %d, %.1f s" % (name, r.nev, r.steps, r.deg, r.t_total))
+    assert r.nev == len(truth) and len(truth) > 0
+    assert np.max(np.abs(r.eigval - truth) / truth) < 1e-10
 
 
 def test_f90_abi_with_host_callbacks(nm):
@@ -302,6 +376,44 @@ def test_f90_abi_with_host_callbacks(nm):
     nm.pevsl_finish_f90_(C.byref(pAB))
 
 
+def test_lanbounds_bounded_basis_and_breakdown(nm, monkeypatch):
+    """LanTrbounds replacement (src/mod_matvec.f90:85,162): (a) with the basis capped far below the step count the
+    explicit restart still returns tight OUTER bounds; (b) an exact breakdown (3 distinct eigenvalues: the Krylov
+    space is exhausted after 3 steps) returns the exact spectrum ends instead of failing."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from oracle import fem
+    from normalmodes_b200 import matvec as mv
+    from normalmodes_b200._lib import check, dptr
+    c = load_case("const3k_p2_j1")
+    Bs, _ = fem.jacobi_scale(c["mats"]["B"])
+    St = fem.to_scipy(Bs)
+    lo = spla.eigsh(St, k=1, which="SA", return_eigenvectors=False)[0]
+    hi = spla.eigsh(St, k=1, which="LA", return_eigenvectors=False)[0]
+    m = mv.COOmat([0, St.shape[0]], Bs["ia"], Bs["ja"], Bs["a"])
+    h = mv.parcsr_create(m)
+    for cap in (None, "24"):
+        if cap:
+            monkeypatch.setenv("NM_LANBOUNDS_MAXCOLS", cap)
+        P = mv.Pevsl(St.shape[0], St.shape[0], 0)
+        P.setamv_op(mv.op_csr(h))
+        lmin, lmax = P.lanbounds(1000, 2000, 1e-12)
+        P.finish()
+        assert lmin <= lo * (1 + 1e-9) and lmax >= hi * (1 - 1e-9), (cap, lmin, lo, lmax, hi)
+        assert lmin >= lo * (0.98 if cap else 1 - 1e-6) and lmax <= hi * (1.01 if cap else 1 + 1e-6), (cap, lmin, lo, lmax, hi)
+    monkeypatch.delenv("NM_LANBOUNDS_MAXCOLS", raising=False)
+    nm.nm_parcsr_free(h)
+    n = 300
+    D = sp.diags(np.tile([1.0, 2.0, 3.0], n // 3)).tocsr()
+    hD = mv.parcsr_create(mv.COOmat([0, n], D.indptr, D.indices, D.data))
+    P = mv.Pevsl(n, n, 0)
+    P.setamv_op(mv.op_csr(hD))
+    lmin, lmax = P.lanbounds(1000, 2000, 1e-12)
+    P.finish()
+    assert abs(lmin - 1.0) < 1e-10 and abs(lmax - 3.0) < 1e-10, (lmin, lmax)
+    nm.nm_parcsr_free(hD)
+
+
 def test_error_paths(nm):
     """Bad input is reported through the status + message, not a crash."""
     from normalmodes_b200 import matvec as mv
@@ -370,9 +482,12 @@ def test_packed_kernel_ring_and_chunking(nm, monkeypatch, sell, entries, distinc
     nm.nm_parcsr_free(h)
 
 
-SLAB_CONFIGS = [dict(), dict(NM_SLAB_PERS="0"), dict(NM_SLAB_PERS_STAGES="2"), dict(NM_SLAB_PERS_STAGES="3", NM_SLAB_MAXGRID="5"),
-                dict(NM_SLAB_PERS_STAGES="4", NM_SLAB_ENTRIES="200", NM_SLAB_DISTINCT="140", NM_SLAB_MAXGRID="3", NM_SLAB_XS="3"),
-                dict(NM_SLAB_THREADS="64", NM_SLAB_ENTRIES="96", NM_SLAB_DISTINCT="140", NM_SLAB_MAXGRID="1", NM_SLAB_PERS_STAGES="2"),
+SLAB_CONFIGS = [dict(), dict(NM_SLAB_PERS="1"), dict(NM_SLAB_PERS="1", NM_SLAB_FLOW="0"), dict(NM_SLAB_PERS="1", NM_SLAB_PERS_STAGES="2"),
+                dict(NM_SLAB_PERS="1", NM_SLAB_PERS_STAGES="3", NM_SLAB_MAXGRID="5"),
+                dict(NM_SLAB_PERS="1", NM_SLAB_FLOW="0", NM_SLAB_PERS_STAGES="3", NM_SLAB_MAXGRID="5"),
+                dict(NM_SLAB_PERS="1", NM_SLAB_PERS_STAGES="4", NM_SLAB_ENTRIES="200", NM_SLAB_DISTINCT="140", NM_SLAB_MAXGRID="3", NM_SLAB_XS="3"),
+                dict(NM_SLAB_PERS="1", NM_SLAB_THREADS="64", NM_SLAB_ENTRIES="96", NM_SLAB_DISTINCT="140", NM_SLAB_MAXGRID="1", NM_SLAB_PERS_STAGES="2"),
+                dict(NM_SLAB_PERS="1", NM_SLAB_FLOW="0", NM_SLAB_THREADS="64", NM_SLAB_ENTRIES="96", NM_SLAB_DISTINCT="140", NM_SLAB_MAXGRID="1", NM_SLAB_PERS_STAGES="2"),
                 dict(NM_SLAB_WS="0"), dict(NM_SLAB_THREADS="64", NM_SLAB_STAGES="3"),
                 dict(NM_SLAB_THREADS="128", NM_SLAB_SPLIT="32", NM_SLAB_STAGES="4", NM_SLAB_XS="2", NM_SLAB_PRODUCERS="1"),
                 dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="8", NM_SLAB_PRODUCERS="8"), dict(NM_SLAB_PRODUCERS="2", NM_SLAB_PDL="0"), dict(NM_SLAB_STAGES="3", NM_SLAB_XS="3"),
@@ -389,7 +504,8 @@ SLAB_CONFIGS = [dict(), dict(NM_SLAB_PERS="0"), dict(NM_SLAB_PERS_STAGES="2"), d
 @pytest.mark.parametrize("cfg", SLAB_CONFIGS)
 def test_chebiter_slab_kernel_configs(nm, monkeypatch, cfg):
     """Fused Chebyshev step through k_slabws / k_slab (TMA ring, cp.async x staging, thread-per-row walk, split rows,
-    warp-specialised producers with full/empty mbarriers) on the
+    warp-specialised producers with full/empty mbarriers) and the whole iteration through the persistent kernel k_slabpers
+    (pinned + ring stages, grid barrier or per-chunk dataflow flags) on the
     KRON3 B~ (P1 and P2) and the CSR Ap~, with chunk sizes / grid limits that force many chunks per CTA (ring
     wrap-around, mbarrier phase flips), against the oracle's Chebyshev iteration; k_pack / k_sell stay covered."""
     from oracle import fem, solver
@@ -398,7 +514,7 @@ def test_chebiter_slab_kernel_configs(nm, monkeypatch, cfg):
     for k, v in cfg.items():
         monkeypatch.setenv(k, v)
     want = dict(pack=1, sell=2).get(cfg.get("NM_CHEB_KERNEL", "slab"),
-                                    3 if cfg.get("NM_SLAB_WS") == "0" else (4 if cfg.get("NM_SLAB_PERS") == "0" else 5))
+                                    3 if cfg.get("NM_SLAB_WS") == "0" else (5 if cfg.get("NM_SLAB_PERS") == "1" else 4))
     for name, key, sign in (("const3k_p2_j1", "B", 1.0), ("prem3k_p1_j2", "B", 1.0), ("prem3k_p2_j2", "Ap", -1.0)):
         c = load_case(name)
         m = to_coomat(c["mats"])[key]

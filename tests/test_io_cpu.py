@@ -23,6 +23,10 @@ def test_output_names_follow_mod_para():
     assert n["fvlist"] == "out/CONST_1L_3k.1_pod1_np2_vlist.dat"
     assert n["fvstat"] == "out/CONST_1L_3k.1_pod1_np2_vstat.dat"
     assert n["fvdata"] == "out/CONST_1L_3k.1_JOB1_pod1_np2_0.200000003_2.00000000"
+    # gfortran's list-directed REAL(4): 9 significant digits, F form on [0.1, 1e9), ES form outside
+    for v, txt in ((0.05, "5.00000007E-02"), (10.0, "10.0000000"), (12.5, "12.5000000"), (0.1, "0.100000001"),
+                   (1.0, "1.00000000"), (123.456, "123.456001")):
+        assert io._list_directed_real4(v) == txt, (v, io._list_directed_real4(v))
 
 
 def test_rank_slices_assemble_the_reference_files(tmp_path):

@@ -30,11 +30,11 @@ def main():
         for _ in range(3):
             check(L.nm_chebiter_solve_dev(cheb, C.c_void_p(z.data_ptr()), C.c_void_p(y.data_ptr())))
         torch.cuda.synchronize()
-        cap = 4096 * 64 * 8
+        cap = 4096 * 256 * 8
         buf = np.zeros(cap, dtype=np.int64); grid = C.c_int(); cf = np.zeros(4097, dtype=np.int32)
         check(L.nm_chebiter_trace_dump(cheb, buf.ctypes.data_as(C.POINTER(C.c_longlong)), cap, C.byref(grid), cf.ctypes.data_as(C.POINTER(C.c_int))))
         g = grid.value
-        T = buf[:g * 64 * 8].reshape(g, 64, 8)
+        T = buf[:g * 256 * 8].reshape(g, 256, 8)      # NM_SLAB_MAXDESC chunks per CTA
         nm = np.diff(cf[:g + 1])
         names = ["0 start->blob(it+1) arrived", "1->2 gather issue", "2->3 epi.load issue", "3->4 walk", "4->5 shuffles+epilogue",
                  "5->6 cp.async wait", "6->7 barrier", "7->next start"]
