@@ -47,7 +47,7 @@ def parse(argv=None):
                    help="ChebAv degree steps per bench step (0: a whole filter application)")
     p.add_argument("--check-steps", type=int, default=2, help="degree steps compared with the CPU oracle (0: no check)")
     p.add_argument("--solve", action="store_true", help="also run the full eigen-solve (time-to-all-eigenpairs)")
-    p.add_argument("--cpu-seconds", type=float, default=8.0, help="target CPU work of one cpu_baseline / reference sample")
+    p.add_argument("--cpu-seconds", type=float, default=6.0, help="target CPU work of one cpu_baseline / reference sample")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--e2e-steps", type=int, default=2, help="bench steps timed through the host-vector C ABI")
     return p.parse_args(argv)

@@ -86,25 +86,87 @@ static void cheb_build_ppack(NmChebIter& C) {
     C.pers_multi_ok = sym;
     for (int& v : sidx) v = R * newid[v / R] + v % R;
     C.send_idx_p.from_host(sidx);
-    if (sym) {
-      const int P = nm_ctx().nranks;
-      std::vector<int> cnt(n + 1, 0);
-      for (int v : sidx) cnt[v / R + 1]++;
-      for (int i = 0; i < n; ++i) cnt[i + 1] += cnt[i];
-      std::vector<NmPushEnt> ent(sidx.size());
-      std::vector<int> fill(cnt.begin(), cnt.end() - 1);
-      for (int r = 0; r < P; ++r)
-        for (int i = M.halo.send_off[r]; i < M.halo.send_off[r + 1]; ++i) {
-          const int v = sidx[i];
-          NmPushEnt e;
-          e.dst = (unsigned)(M.halo.peer_base[r] + (i - M.halo.send_off[r]));
-          e.peer = (unsigned short)r; e.comp = (unsigned short)(v % R);
-          ent[fill[v / R]++] = e;
-        }
-      C.push_off.from_host(cnt);
-      C.push_ent.alloc(std::max<size_t>(ent.size(), 1)); C.push_ent.upload(ent.data(), ent.size());
+    C.h_sidx_p = sidx;                                           // the push tables follow once every rank agrees
+  }
+}
+
+// Slot numbering + push tables of the in-kernel exchange (collective: every rank, after the common decision).
+// WHERE a boundary value lands in the receiver's slot buffer is free as long as both sides agree, and it decides how
+// many NVLink write transactions a step costs: with the receiver's natural order (sorted by global id) the 16-byte
+// stores of a warp's epilogue scatter -- one transaction per value, and the SM's queue of outstanding peer writes
+// (not the link) bounds the step: 200k-tet workload on 2 GPUs, 30 k values per step, B~ step 32 us whatever the
+// matrix size (profiles/r2e_*).  Here the block of sender s in the receiver's buffer is laid out in the SENDER's pack
+// order, component-major: the k-th boundary node sent to a peer (pack order) owns slots {k, K + k, 2K + k}, so the
+// lanes of a warp that send component c of consecutive boundary rows write CONSECUTIVE slots (coalesced into full
+// lines).  The receiver learns the layout once (its ghost column -> slot table, gathered through with one indirection).
+static void cheb_build_push_tables(NmChebIter& C) {
+  NmParcsr& M = *C.M;
+  NmHalo& h = M.halo;
+  NmCtx& c = nm_ctx();
+  const int P = c.nranks, R = M.format == NM_FMT_KRON3 ? 3 : 1;
+  const int n = M.format == NM_FMT_KRON3 ? M.nbrow : M.nrow;
+  const std::vector<int>& sidx = C.h_sidx_p;
+  std::vector<int> newslot(std::max(h.nsend, 1), 0);
+  // NM_LL_PACKORDER=1: the layout described above.  Default 0 = the receiver's natural order (no indirection in the
+  // gather): measured on the 200k-tet workload on 2 GPUs the coalesced stores bought nothing and the extra dependent
+  // load in the boundary chunks' gather cost 6 us per B~ step (profiles/r2h_*) -- the stores were not the limiter.
+  const bool packorder = nm_env_int("NM_LL_PACKORDER", 0) != 0;
+  for (int r = 0; r < P; ++r) {
+    const int o0 = h.send_off[r], o1 = h.send_off[r + 1];
+    if (o1 == o0) continue;
+    if (!packorder) { for (int i = o0; i < o1; ++i) newslot[i] = i - o0; continue; }
+    std::vector<int> rows;
+    for (int i = o0; i < o1; ++i) rows.push_back(sidx[i] / R);
+    std::sort(rows.begin(), rows.end());
+    rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+    const int K = (int)rows.size();
+    NM_REQUIRE(o1 - o0 == R * K, "in-kernel halo: a boundary node is sent with %d of its %d components", (o1 - o0), R * K);
+    for (int i = o0; i < o1; ++i) {
+      const int k = (int)(std::lower_bound(rows.begin(), rows.end(), sidx[i] / R) - rows.begin());
+      newslot[i] = (sidx[i] % R) * K + k;
     }
   }
+  // tell every receiver where its ghosts from this rank sit inside this rank's block
+  DBuf<int> d_send(std::max(h.nsend, 1)), d_recv(std::max(h.nghost, 1));
+  if (h.nsend) d_send.upload(newslot.data(), h.nsend);
+  NM_NCCL(ncclGroupStart());
+  for (int r = 0; r < P; ++r) {
+    if (r == c.rank) continue;
+    if (h.send_cnt[r] > 0) NM_NCCL(ncclSend(d_send.p + h.send_off[r], h.send_cnt[r], ncclInt, r, c.nccl, c.stream));
+    if (h.recv_cnt[r] > 0) NM_NCCL(ncclRecv(d_recv.p + h.recv_off[r], h.recv_cnt[r], ncclInt, r, c.nccl, c.stream));
+  }
+  NM_NCCL(ncclGroupEnd());
+  std::vector<int> gslot(std::max(h.nghost, 1), 0);
+  if (h.nghost) d_recv.download(gslot.data(), h.nghost);
+  else NM_CUDA(cudaStreamSynchronize(c.stream));
+  for (int r = 0; r < P; ++r) {
+    std::vector<char> seen(h.recv_cnt[r], 0);
+    for (int g = h.recv_off[r]; g < h.recv_off[r + 1]; ++g) {
+      NM_REQUIRE(gslot[g] >= 0 && gslot[g] < h.recv_cnt[r] && !seen[gslot[g]], "in-kernel halo: rank %d sent a bad slot layout", r);
+      seen[gslot[g]] = 1;
+      gslot[g] += h.recv_off[r];
+    }
+  }
+  if (packorder) C.ghost_slot.from_host(gslot);
+  if (h.nsend == 0) return;
+  std::vector<int> sslot(h.nsend);
+  std::vector<int> cnt(n + 1, 0);
+  for (int v : sidx) cnt[v / R + 1]++;
+  for (int i = 0; i < n; ++i) cnt[i + 1] += cnt[i];
+  std::vector<NmPushEnt> ent(sidx.size());
+  std::vector<int> fill(cnt.begin(), cnt.end() - 1);
+  for (int r = 0; r < P; ++r)
+    for (int i = h.send_off[r]; i < h.send_off[r + 1]; ++i) {
+      const int v = sidx[i];
+      sslot[i] = h.peer_base[r] + newslot[i];
+      NmPushEnt e;
+      e.dst = (unsigned)sslot[i];
+      e.peer = (unsigned short)r; e.comp = (unsigned short)(v % R);
+      ent[fill[v / R]++] = e;
+    }
+  C.send_slot.from_host(sslot);
+  C.push_off.from_host(cnt);
+  C.push_ent.alloc(std::max<size_t>(ent.size(), 1)); C.push_ent.upload(ent.data(), ent.size());
 }
 
 // In-kernel halo on several GPUs (collective decision, every rank takes the same branch) and the opt-in persistent
@@ -126,6 +188,7 @@ static void cheb_setup_multi_pers(NmChebIter& C) {
     d.download(&v, 1);
     ll_ok = v > 0.5;
     if (ll_ok) ll_ok = nm_halo_ll_setup(M.halo);
+    if (ll_ok) cheb_build_push_tables(C);
     C.fused = ll_ok;
   }
   // NM_SLAB_PERS: 0 (default) one launch per step chained by programmatic dependent launch; 1 the whole iteration in one
@@ -160,7 +223,7 @@ static void cheb_step_fused(NmChebIter& C, const double* din, const EpiCheb& e, 
   if (h.nsend > 0) {
     const unsigned tin = tag0 + (unsigned)k;
     F.ll_in = (const unsigned long long*)(c.win + h.win_ll[tin % 3u]);
-    F.tag_in = tin; F.status = c.dev_status;
+    F.tag_in = tin; F.status = c.dev_status; F.gslot = C.ghost_slot.p;
     static const int dbg = nm_env_int("NM_DEBUG_LL", 0);
     F.debug = dbg;
     if (k < C.deg - 1) {
@@ -236,13 +299,13 @@ void nm_chebiter_solve(NmChebIter& C, const double* b, double* x) {
     if (c.nranks > 1 && h.nsend > 0) {
       const unsigned long long e0 = ++h.epoch;
       W.tag0 = (unsigned)e0;
-      nm_halo_push_ll(M, b, C.send_idx_p.p, W.tag0, (int)(W.tag0 % 3u));
+      nm_halo_push_ll(M, b, C.send_idx_p.p, C.send_slot.p, W.tag0, (int)(W.tag0 % 3u));
       for (int q = 0; q < 3; ++q) {
         W.ll_in[q] = (const unsigned long long*)(c.win + h.win_ll[q]);
         for (int r = 0; r < c.nranks; ++r)
           if (r != c.rank && h.send_cnt[r] > 0) W.ll_out[q][r] = (unsigned long long*)(c.peer_win[r] + h.peer_ll[q][r]);
       }
-      W.push_off = C.push_off.p; W.push_ent = C.push_ent.p; W.hstatus = c.dev_status;
+      W.push_off = C.push_off.p; W.push_ent = C.push_ent.p; W.hstatus = c.dev_status; W.gslot = C.ghost_slot.p;
       h.epoch = e0 + (unsigned long long)(C.deg - 1);
     }
     bool launched = true;
@@ -272,7 +335,7 @@ void nm_chebiter_solve(NmChebIter& C, const double* b, double* x) {
     // boundary values of b -> the peers' slots (what step 0 gathers); deg epochs for the solve
     const unsigned long long e0 = ++M.halo.epoch;
     fused_tag0 = (unsigned)e0;
-    nm_halo_push_ll(M, b, C.send_idx_p.p, fused_tag0, (int)(fused_tag0 % 3u));
+    nm_halo_push_ll(M, b, C.send_idx_p.p, C.send_slot.p, fused_tag0, (int)(fused_tag0 % 3u));
     M.halo.epoch = e0 + (unsigned long long)(C.deg - 1);
   }
   for (int k = 0; k < C.deg; ++k) {

@@ -270,6 +270,9 @@ struct NmChebIter {
   bool pers_multi_ok = false;             // the halo pattern allows the in-kernel exchange (symmetric)
   DBuf<int> push_off;
   DBuf<NmPushEnt> push_ent;
+  std::vector<int> h_sidx_p;              // host copy of send_idx_p
+  DBuf<int> ghost_slot;                   // ghost column (position in the ghost tail) -> slot in this rank's buffers
+  DBuf<int> send_slot;                    // send-list entry -> slot in the receiving peer's buffers
   DBuf<double> ak_dev, bk_dev;
   DBuf<unsigned long long> gbar;          // grid-barrier counter of the persistent kernel (monotonic)
   unsigned long long gbar_base = 0;
@@ -336,7 +339,7 @@ void nm_halo_exchange(NmParcsr& M, const double* x, const int* send_idx = nullpt
 struct NmHaloWait { const unsigned long long* flags; unsigned mask; unsigned long long epoch; int* status; };
 bool nm_halo_push_nowait(NmParcsr& M, const double* x, const int* send_idx, NmHaloWait* w);
 bool nm_halo_ll_setup(NmHalo& h);            // collective: LL ghost slots in the peer window; false without a window
-void nm_halo_push_ll(NmParcsr& M, const double* x, const int* send_idx, unsigned tag, int buf);
+void nm_halo_push_ll(NmParcsr& M, const double* x, const int* send_idx, const int* send_slot, unsigned tag, int buf);
 void nm_spmv(NmParcsr& M, const double* x, double* y);                 // y = M x   (device pointers)
 void nm_spmv_add(NmParcsr& M, const double* x, double* y);             // y += M x
 // packed format (nm_pack.cu): rp/idx = host row pointers and column ids of the chosen format, n (block-)rows

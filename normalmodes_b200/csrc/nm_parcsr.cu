@@ -148,14 +148,15 @@ struct NmPushLLArgs {
   unsigned long long* peer_ll[8];           // this rank's block of slots in each peer's buffer
   unsigned tag;
 };
-__global__ void k_halo_push_ll(NmPushLLArgs A, const double* __restrict__ x, const int* __restrict__ idx) {
+__global__ void k_halo_push_ll(NmPushLLArgs A, const double* __restrict__ x, const int* __restrict__ idx,
+                               const int* __restrict__ slot) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.nsend; i += gridDim.x * blockDim.x) {
     int r = 0;
     while (i >= A.send_off[r + 1]) ++r;
-    nm_ll_store(A.peer_ll[r] + 2 * (size_t)(i - A.send_off[r]), x[idx[i]], A.tag);
+    nm_ll_store(A.peer_ll[r] + 2 * (size_t)slot[i], x[idx[i]], A.tag);
   }
 }
-void nm_halo_push_ll(NmParcsr& M, const double* x, const int* send_idx, unsigned tag, int buf) {
+void nm_halo_push_ll(NmParcsr& M, const double* x, const int* send_idx, const int* send_slot, unsigned tag, int buf) {
   NmCtx& c = nm_ctx();
   NmHalo& h = M.halo;
   if (h.nsend == 0) return;
@@ -166,9 +167,9 @@ void nm_halo_push_ll(NmParcsr& M, const double* x, const int* send_idx, unsigned
   for (int r = 0; r <= 8; ++r) A.send_off[r] = h.send_off[std::min(r, c.nranks)];
   for (int r = 0; r < c.nranks; ++r)
     if (r != c.rank && h.send_cnt[r] > 0)
-      A.peer_ll[r] = (unsigned long long*)(c.peer_win[r] + h.peer_ll[buf][r]) + 2 * (size_t)h.peer_base[r];
+      A.peer_ll[r] = (unsigned long long*)(c.peer_win[r] + h.peer_ll[buf][r]);     // send_slot includes the block's base
   const int blocks = std::max(1, std::min(32, nm_div_up(h.nsend, 1024)));
-  k_halo_push_ll<<<blocks, 256, 0, c.stream>>>(A, x, send_idx ? send_idx : (const int*)h.send_idx.p);
+  k_halo_push_ll<<<blocks, 256, 0, c.stream>>>(A, x, send_idx ? send_idx : (const int*)h.send_idx.p, send_slot);
   c.launches++;
 }
 bool nm_halo_ll_setup(NmHalo& h) {

@@ -516,21 +516,51 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
     H.cta_first[grid] = ci;
     NM_REQUIRE(ci == nchunk, "slab: chunk split lost chunks (%d of %d)", ci, nchunk);
   }
-  // processing order inside a CTA's range: chunks without ghost columns first, so that on several GPUs the chunks
-  // that need the peers' values come last and the halo exchange overlaps the interior ones (the row positions are in
-  // the blob headers: the order of the descriptors is free)
+  // Several GPUs: a chunk with ghost columns costs more than its bytes (its ghost values are polled out of the
+  // flag-in-data slots through registers, its boundary rows are stored to the peers), and the chunks next to a
+  // partition boundary are neighbours in the breadth-first order -- a contiguous split hands ALL of them to a few CTAs,
+  // whose tail then sets the step time (200k-tet workload on 2 GPUs: B~ step 32 us for half the rows of the 28 us
+  // single-GPU step, with or without waiting for the peer: profiles/r2e_*).  So the two kinds are dealt separately:
+  // every CTA gets a contiguous share of the interior chunks (by bytes) followed by a contiguous share of the boundary
+  // chunks (by bytes).  The processing order inside a CTA stays "interior first": the values the boundary chunks need
+  // were sent a whole step earlier.  (The row positions are in the blob headers: the order of the descriptors is free.)
   H.desc_cid.resize(nchunk);
-  for (int g = 0; g < grid; ++g) {
-    std::vector<NmPackDesc> in, bd;
+  {
     std::vector<int> in_id, bd_id;
-    for (int ci = H.cta_first[g]; ci < H.cta_first[g + 1]; ++ci) {
-      (ghost_chunk[ci] ? bd : in).push_back(desc[ci]);
-      (ghost_chunk[ci] ? bd_id : in_id).push_back(ci);
+    for (int ci = 0; ci < nchunk; ++ci) (ghost_chunk[ci] ? bd_id : in_id).push_back(ci);
+    std::vector<std::vector<int>> mine(grid);
+    bool dealt = !bd_id.empty() && nm_env_int("NM_SLAB_DEAL_GHOST", 0) != 0;
+    if (dealt) {
+      auto deal = [&](const std::vector<int>& ids) {
+        size_t tot = 0, cum = 0;
+        for (int ci : ids) tot += desc[ci].bytes;
+        for (int ci : ids) {
+          const int g = (int)std::min<size_t>((size_t)grid - 1, (size_t)((double)(cum + desc[ci].bytes / 2) / (double)std::max<size_t>(tot, 1) * grid));
+          mine[g].push_back(ci);
+          cum += desc[ci].bytes;
+        }
+      };
+      deal(in_id); deal(bd_id);
+      for (int g = 0; g < grid && dealt; ++g) dealt = !mine[g].empty() && (int)mine[g].size() <= maxper;
     }
-    std::copy(in.begin(), in.end(), desc.begin() + H.cta_first[g]);
-    std::copy(bd.begin(), bd.end(), desc.begin() + H.cta_first[g] + in.size());
-    std::copy(in_id.begin(), in_id.end(), H.desc_cid.begin() + H.cta_first[g]);
-    std::copy(bd_id.begin(), bd_id.end(), H.desc_cid.begin() + H.cta_first[g] + in_id.size());
+    if (!dealt) {                                                // one GPU, or a matrix too small to deal: contiguous ranges
+      for (int g = 0; g < grid; ++g) {
+        mine[g].clear();
+        for (int ci = H.cta_first[g]; ci < H.cta_first[g + 1]; ++ci) if (!ghost_chunk[ci]) mine[g].push_back(ci);
+        for (int ci = H.cta_first[g]; ci < H.cta_first[g + 1]; ++ci) if (ghost_chunk[ci]) mine[g].push_back(ci);
+      }
+    }
+    std::vector<NmPackDesc> nd(nchunk);
+    int pos = 0;
+    H.max_chunks_per_cta = 0;
+    for (int g = 0; g < grid; ++g) {
+      H.cta_first[g] = pos;
+      for (int ci : mine[g]) { nd[pos] = desc[ci]; H.desc_cid[pos] = ci; ++pos; }
+      H.max_chunks_per_cta = std::max(H.max_chunks_per_cta, (int)mine[g].size());
+    }
+    H.cta_first[grid] = pos;
+    NM_REQUIRE(pos == nchunk, "slab: chunk deal lost chunks (%d of %d)", pos, nchunk);
+    desc = nd;
   }
   H.grid = grid;
   H.padded_entries = pentries;

@@ -239,6 +239,7 @@ struct NmSlabFusedArgs {
   unsigned long long* ll_out[8];        // this rank's block of slots in each peer's buffer of tag_out
   const unsigned long long* ll_in;      // this rank's ghost slots of tag_in (null: no ghosts gathered through slots)
   unsigned tag_in, tag_out;
+  const int* gslot;             // ghost column -> slot
   int* status;
   int debug;                    // NM_DEBUG_LL bit 0: no tag wait (timing diagnostics only)
 };
@@ -264,17 +265,19 @@ __device__ __forceinline__ void nm_slab_gather_ghost(const NmSlabView& v, double
 
 template <int R>
 __device__ __forceinline__ void nm_slab_gather_ll(const NmSlabView& v, double* xs, const double* __restrict__ x,
-                                                  const unsigned long long* ll, unsigned tag, int* status, int ncol,
-                                                  int t, int nthreads, bool nowait = false) {
+                                                  const unsigned long long* ll, const int* __restrict__ gslot, unsigned tag,
+                                                  int* status, int ncol, int t, int nthreads, bool nowait = false,
+                                                  int lmode = 0) {
   const int tot = R * v.h.nd;
-  // 4 independent column ids / slot loads in flight per thread: a ghost value is a dependent 16-byte L2 load, and a
+  // LLB independent column ids / slot loads in flight per thread: a ghost value is a dependent 16-byte L2 load, and a
   // boundary chunk has hundreds of them.  NM_DEBUG_LL (diagnostics, bit 0): do not wait for the tags (timing of the
   // kernel without the exchange latency; results are then wrong)
-  for (int j = t; j < tot; j += 4 * nthreads) {
-    int cc[4];
-    unsigned a[4], fa[4], b[4], fb[4];
+  constexpr int LLB = 2;
+  for (int j = t; j < tot; j += LLB * nthreads) {
+    int cc[LLB];
+    unsigned a[LLB], fa[LLB], b[LLB], fb[LLB];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < LLB; ++u) {
       const int jj = j + u * nthreads;
       cc[u] = -1;
       if (jj < tot) {
@@ -282,17 +285,20 @@ __device__ __forceinline__ void nm_slab_gather_ll(const NmSlabView& v, double* x
         cc[u] = R * v.scols[node] + (jj - R * node);
       }
     }
+    if (gslot) {                                                 // ghost column -> its slot (sender's pack order layout)
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < LLB; ++u) if (cc[u] >= ncol) cc[u] = ncol + gslot[cc[u] - ncol];
+    }
+#pragma unroll
+    for (int u = 0; u < LLB; ++u) {
       const int jj = j + u * nthreads;
       fa[u] = fb[u] = tag; a[u] = b[u] = 0u;
       if (cc[u] < 0) continue;
       if (cc[u] < ncol) { nm_cp_async8(xs + jj, x + cc[u]); continue; }
-      asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                   : "=r"(a[u]), "=r"(fa[u]), "=r"(b[u]), "=r"(fb[u]) : "l"(ll + 2 * (size_t)(cc[u] - ncol)) : "memory");
+      nm_ll_load_raw(ll + 2 * (size_t)(cc[u] - ncol), lmode, a[u], fa[u], b[u], fb[u]);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < LLB; ++u) {
       if (cc[u] < ncol) continue;                                // nothing (-1) or an owned column (cp.async above)
       double val = __longlong_as_double((long long)(((unsigned long long)b[u] << 32) | a[u]));
       if ((fa[u] != tag || fb[u] != tag) && !nowait) {
@@ -366,7 +372,7 @@ __global__ void __launch_bounds__(32 * (NC + 8)) k_slabws(NmSlabWsArgs W, Epi ep
       const NmSlabView v = nm_slab_view(stage0 + (size_t)s * A.stage_bytes);
       double* xs = xs0 + (size_t)xb * A.xs_doubles;
       if (FUSED && v.h.has_ghost && F.ll_in) {
-        nm_slab_gather_ll<R>(v, xs, x, F.ll_in, F.tag_in, F.status, ncol, ptid, pthreads, (F.debug & 1) != 0);
+        nm_slab_gather_ll<R>(v, xs, x, F.ll_in, F.gslot, F.tag_in, F.status, ncol, ptid, pthreads, (F.debug & 1) != 0, (F.debug >> 2) & 3);
       } else if (v.h.has_ghost && W.hmask) {
         if (!flags_seen) {
           if (lane == 0) {
@@ -456,14 +462,14 @@ __global__ void __launch_bounds__(32 * (NC + 8)) k_slabws(NmSlabWsArgs W, Epi ep
         double dn[R];
 #pragma unroll
         for (int c = 0; c < R; ++c) dn[c] = epi.apply_dn(row0 + c, acc[c], in[c]);
-        if (F.push_off) {
+        if (F.push_off && v.h.has_ghost) {                        // symmetric pattern: sent rows gather ghost columns
           const int prow = v.h.first + (int)(lw & 0x3ffu);
           for (int e = F.push_off[prow]; e < F.push_off[prow + 1]; ++e) {
             const NmPushEnt pe = F.push_ent[e];
             double val = dn[0];
 #pragma unroll
             for (int c = 1; c < R; ++c) if (pe.comp == c) val = dn[c];
-            nm_ll_store(F.ll_out[pe.peer] + 2 * (size_t)pe.dst, val, F.tag_out);
+            if (!(F.debug & 2)) nm_ll_store_mode(F.ll_out[pe.peer] + 2 * (size_t)pe.dst, val, F.tag_out, (F.debug >> 4) & 3);   // bit 1: timing without the stores
           }
         }
       } else {
@@ -508,6 +514,7 @@ struct NmSlabPersArgs {
   const unsigned long long* ll_in[3];   // this rank's ghost slots, by tag % 3
   unsigned long long* ll_out[3][8];     // this rank's block of slots in each peer's buffers
   const int* push_off; const NmPushEnt* push_ent;
+  const int* gslot;         // ghost column -> slot
   unsigned tag0;            // tag of the values step 0 gathers (pushed by nm_halo_push_ll)
   int* hstatus;
 };
@@ -648,7 +655,7 @@ __global__ void __launch_bounds__(32 * (NC + 9)) k_slabpers(NmSlabPersArgs W) {
         }
         if (gx >= X) nm_mbar_wait_bounded(empty_xs + xb, (uint32_t)(((gx / X) - 1) & 1));
         double* xs = xs0 + (size_t)xb * A.xs_doubles;
-        if (multi && v.h.has_ghost) nm_slab_gather_ll<R>(v, xs, x, ll, tag, W.hstatus, ncol, ptid, pthreads);
+        if (multi && v.h.has_ghost) nm_slab_gather_ll<R>(v, xs, x, ll, W.gslot, tag, W.hstatus, ncol, ptid, pthreads);
         else nm_slab_gather<R>(v, xs, x, x, ncol, ptid, pthreads);
         nm_cp_async_mbar_arrive_noinc(full_xs + xb);
         if (ptid == 0 && RG) pump(-1);
@@ -727,7 +734,7 @@ __global__ void __launch_bounds__(32 * (NC + 9)) k_slabpers(NmSlabPersArgs W) {
         double dn[R];
 #pragma unroll
         for (int c = 0; c < R; ++c) dn[c] = epi.apply_dn(row0 + c, acc[c], in[c]);
-        if (push) {
+        if (push && v.h.has_ghost) {                              // symmetric pattern: sent rows gather ghost columns
           for (int e = W.push_off[prow]; e < W.push_off[prow + 1]; ++e) {
             const NmPushEnt pe = W.push_ent[e];
             double val = dn[0];

@@ -172,6 +172,24 @@ __device__ __forceinline__ void nm_ll_store(unsigned long long* slot, double v, 
   const unsigned long long w1 = (u >> 32) | ((unsigned long long)tag << 32);
   asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
 }
+// variants for measurements (NM_DEBUG_LL bits 2-4): 0 volatile = relaxed.sys (default), 1 ld.global.cg (weak, L2),
+// 2 ld.relaxed.gpu
+__device__ __forceinline__ void nm_ll_load_raw(const unsigned long long* slot, int mode, unsigned& a, unsigned& fa, unsigned& b, unsigned& fb) {
+  if (mode == 1)
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(slot) : "memory");
+  else if (mode == 2)
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(slot) : "memory");
+  else
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(slot) : "memory");
+}
+__device__ __forceinline__ void nm_ll_store_mode(unsigned long long* slot, double v, unsigned tag, int mode) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long w0 = (u & 0xffffffffull) | ((unsigned long long)tag << 32);
+  const unsigned long long w1 = (u >> 32) | ((unsigned long long)tag << 32);
+  if (mode == 1) asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+  else if (mode == 2) asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+  else asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+}
 __device__ __forceinline__ bool nm_ll_load(const unsigned long long* slot, unsigned tag, double* v) {
   unsigned a, fa, b, fb;
   asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(slot) : "memory");

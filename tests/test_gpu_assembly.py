@@ -76,4 +76,18 @@ def test_end_to_end_from_mesh_files_prem_like(nm):
     truth = solver.truth_eigs(mats, r.xintv[0], r.xintv[1])
     assert r.nev == len(truth) and r.nev > 5
     assert np.max(np.abs(r.eigval - truth) / truth) < 1e-10
+    # the reference's result files (src/mod_pevsl.f90:188-201,225-243) written from the GPU solve and read back: eigenvector i
+    # in physical coordinates x = d * y is an eigenvector of the UNSCALED oracle pencil
+    import tempfile
+    from normalmodes_b200 import io
+    with tempfile.TemporaryDirectory() as tmp:
+        names = io.output_names(tmp + "/", "prem_like", 2, 1, 1, 0.3, 1.2)
+        files = pevsl.pnm_save_eigenvectors(m, r, names["fvdata"])
+        assert len(files) == r.nev and files[0].endswith("_0.300000012_1.20000005_1.dat")
+        A, B = solver.effective_pencil(mats)
+        for i in (0, r.nev // 2, r.nev - 1):
+            x = np.fromfile(files[i], dtype="<f8")
+            assert x.size == m.Gpbsiz
+            res = np.linalg.norm(A @ x - r.eigval[i] * (B @ x)) / (abs(r.eigval[i]) * np.linalg.norm(B @ x))
+            assert res < 1e-7, (i, res)
     f.free()
