@@ -529,7 +529,7 @@ static bool slab_build_host(NmSlabHost& H, const std::vector<int>& rp, const std
     std::vector<int> in_id, bd_id;
     for (int ci = 0; ci < nchunk; ++ci) (ghost_chunk[ci] ? bd_id : in_id).push_back(ci);
     std::vector<std::vector<int>> mine(grid);
-    bool dealt = !bd_id.empty() && nm_env_int("NM_SLAB_DEAL_GHOST", 0) != 0;
+    bool dealt = !bd_id.empty() && nm_env_int("NM_SLAB_DEAL_GHOST", 1) != 0;
     if (dealt) {
       auto deal = [&](const std::vector<int>& ids) {
         size_t tot = 0, cum = 0;
