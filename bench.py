@@ -434,7 +434,7 @@ def main():
         kind = C.c_int(); pbytes = C.c_longlong()
         _lib.check(L.nm_chebiter_pack_info(cheb, C.byref(kind), C.byref(pbytes)))
         return kind.value, pbytes.value
-    knames = ("k_spmv_kron3<EpiCheb>", "k_pack<KRON3,EpiCheb>", "k_sell<KRON3,EpiCheb>", "k_slab<3,256,EpiCheb>",
+    knames = ("k_spmv_kron3<EpiCheb>", "(retired)", "(retired)", "k_slab<3,256,EpiCheb>",
               "k_slabws<3,8,EpiCheb>", "k_slabpers<3,8>")
     us_solveB = timeit(lambda: _lib.check(L.nm_chebiter_solve_dev(mv.chebB, C.c_void_p(z.data_ptr()), C.c_void_p(y.data_ptr()))), 10)
     us_launch = us_solveB / mv.degB

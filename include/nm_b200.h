@@ -63,7 +63,7 @@ int nm_chebiter_free(void* cheb);
 int nm_chebiter_solve_host(void* cheb, const double* b, double* x);
 int nm_chebiter_solve_dev(void* cheb, const double* b_dev, double* x_dev);
 int nm_chebiter_stats(void* cheb, long long* nsolve, long long* nmatvec, int* deg, double* lmin, double* lmax);
-/* kind: 0 plain kernels, 1 TMA-staged packed kernel, 2 sliced JDS, 3 warp-sliced ELL slabs (k_slab), 4 the same with
+/* kind: 0 plain subwarp kernels (fallback), 1-2 retired, 3 warp-sliced ELL slabs (k_slab), 4 the same with
    producer/consumer warps (k_slabws, one launch per step), 5 the whole iteration in one persistent cooperative launch
    (k_slabpers, default: grid barrier per step, in-kernel flag-in-data halo on several GPUs);
    bytes: matrix bytes one step streams */

@@ -10,7 +10,7 @@ import sysconfig
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnm_b200.so")
-SOURCES = ["nm_runtime.cu", "nm_parcsr.cu", "nm_pack.cu", "nm_slab.cu", "nm_chebiter.cu", "nm_ops.cu", "nm_lanczos.cu", "nm_hostmath.cpp",
+SOURCES = ["nm_runtime.cu", "nm_parcsr.cu", "nm_slab.cu", "nm_chebiter.cu", "nm_ops.cu", "nm_lanczos.cu", "nm_hostmath.cpp",
            "nm_pevsl_f90.cpp", "nm_assembly.cu", "nm_pattern.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

@@ -8,7 +8,7 @@
 #include "nm_slab.cuh"
 #include <algorithm>
 
-// The iteration keeps its vectors in the PACK ORDER of a second, permuted copy of M (nm_pack_build_into): every
+// The iteration keeps its vectors in the PACK ORDER of a second, permuted copy of M (the slabs of nm_slab.cu): every
 // step's epilogue then reads and writes contiguous ranges and the x values a chunk gathers sit in a few
 // contiguous runs.  b is permuted in once and x out once per solve (2 of the deg+2 vector passes).
 __global__ void k_perm_gather(double* __restrict__ dst, const double* __restrict__ src, const int* __restrict__ order,
@@ -36,23 +36,13 @@ static void cheb_build_ppack(NmChebIter& C) {
   (blk ? M.bia : M.ia).download(rp.data(), rp.size());
   idx.resize(rp[n]);
   (blk ? M.bja : M.ja).download(idx.data(), idx.size());
-  const int* order_dev = nullptr;
-  // NM_CHEB_KERNEL: slab (default; k_slab, thread per index row) | pack (k_pack) | sell (k_sell)
+  // NM_CHEB_KERNEL=plain: the subwarp-per-row kernels on the caller's numbering (also the fallback of matrices the
+  // slab packer refuses: a row longer than a warp can share, too many distinct columns for a stage)
   const char* kk = getenv("NM_CHEB_KERNEL");
-  const bool want_slab = !(kk && kk[0]) ? !nm_use_sell() : (strcmp(kk, "slab") == 0);
-  const bool want_sell = (kk && kk[0]) ? (strcmp(kk, "sell") == 0) : nm_use_sell();
-  if (want_slab) nm_slab_build_into(M, C.pslab, rp, idx, n);
-  if (C.pslab.nchunk > 0) {
-    order_dev = C.pslab.order.p;
-  } else if (want_sell) {
-    nm_sell_build_into(M, C.psell, rp, idx, n, true);
-    if (C.psell.nchunk == 0) return;
-    order_dev = C.psell.order.p;
-  } else {
-    nm_pack_build_into(M, C.ppack, rp, idx, n, true);
-    if (C.ppack.nchunk == 0) return;
-    order_dev = C.ppack.order.p;
-  }
+  if (kk && strcmp(kk, "plain") == 0) return;
+  nm_slab_build_into(M, C.pslab, rp, idx, n);
+  if (C.pslab.nchunk == 0) return;
+  const int* order_dev = C.pslab.order.p;
   C.ppack_version = M.values_version;
   C.bp.alloc(std::max(M.nrow, 1)); C.xp.alloc(std::max(M.nrow, 1));
   if (M.halo.nsend > 0) {
@@ -266,13 +256,13 @@ void nm_chebiter_solve(NmChebIter& C, const double* b, double* x) {
   NmParcsr& M = *C.M;
   NmCtx& c = nm_ctx();
   double* dbuf[2] = {C.d0.p, C.d1.p};
-  const bool perm = C.ppack.nchunk > 0 || C.psell.nchunk > 0 || C.pslab.nchunk > 0;
-  const int* order_dev = C.pslab.nchunk > 0 ? C.pslab.order.p : (C.psell.nchunk > 0 ? C.psell.order.p : C.ppack.order.p);
+  const bool perm = C.pslab.nchunk > 0;
+  const int* order_dev = C.pslab.order.p;
   const int nblk = M.format == NM_FMT_KRON3 ? M.nbrow : M.nrow, R = M.format == NM_FMT_KRON3 ? 3 : 1;
   double* xout = x;
   if (perm) {
     if (C.ppack_version != M.values_version) {
-      nm_pack_fill_from(M, C.ppack); nm_sell_fill_from(M, C.psell); nm_slab_fill_from(M, C.pslab);
+      nm_slab_fill_from(M, C.pslab);
       C.ppack_version = M.values_version;
     }
     k_perm_gather<<<nm_div_up(M.nrow, 256), 256, 0, c.stream>>>(C.bp.p, b, order_dev, nblk, R);
@@ -349,8 +339,6 @@ void nm_chebiter_solve(NmChebIter& C, const double* b, double* x) {
     e.inv_theta = 1.0 / C.theta; e.ak = C.ak[k]; e.bk = C.bk[k];
     if (C.fused) cheb_step_fused(C, din, e, k, fused_tag0);
     else if (C.pslab.nchunk > 0) nm_spmv_slab_epi(M, C.pslab, din, e, C.send_idx_p.p);
-    else if (C.psell.nchunk > 0) nm_spmv_sell_epi(M, C.psell, din, e, C.send_idx_p.p);
-    else if (perm) nm_spmv_pack_epi(M, C.ppack, din, e, C.send_idx_p.p);
     else nm_spmv_epi(M, din, e);
     din = dbuf[k & 1];
   }
@@ -391,15 +379,15 @@ extern "C" int nm_chebiter_solve_dev(void* h, const double* b_dev, double* x_dev
   nm_chebiter_solve(*(NmChebIter*)h, b_dev, x_dev);
   NM_API_END
 }
-// kind: 0 = plain kernels on the caller's numbering, 1 = TMA-staged packed kernel (k_pack), 2 = sliced JDS (k_sell),
+// kind: 0 = plain kernels on the caller's numbering (1, 2: the retired round-1a kernels),
 // 3 = TMA-staged warp-sliced ELL slabs (k_slab), 4 = the same, warp-specialised (k_slabws), 5 = the whole iteration in one
 // persistent cooperative launch (k_slabpers, default); all on vectors kept in pack order; bytes = matrix bytes one iteration step streams
 extern "C" int nm_chebiter_pack_info(void* h, int* kind, long long* bytes) {
   NM_API_BEGIN
   NmChebIter& C = *(NmChebIter*)h;
-  const int k = C.pslab.nchunk > 0 ? (C.pers ? 5 : (C.pslab.ws ? 4 : 3)) : (C.psell.nchunk > 0 ? 2 : (C.ppack.nchunk > 0 ? 1 : 0));
+  const int k = C.pslab.nchunk > 0 ? (C.pers ? 5 : (C.pslab.ws ? 4 : 3)) : 0;
   if (kind) *kind = k;
-  if (bytes) *bytes = k >= 3 ? C.pslab.bytes : (k == 2 ? C.psell.bytes : (k == 1 ? C.ppack.bytes : C.M->fmt_bytes));
+  if (bytes) *bytes = k >= 3 ? C.pslab.bytes : C.M->fmt_bytes;
   NM_API_END
 }
 // diagnostic (NM_SLAB_TRACE=1): clock64 stamps of the last k_slab launch, [grid][64 chunks][8 stamps]; returns grid

@@ -151,44 +151,7 @@ struct NmHalo {
   }
 };
 
-// Packed row-block format of the streaming SpMV (nm_spmv.cuh / nm_pack.cu).  The (block-)rows are ordered for
-// locality (Cuthill-McKee on the block pattern) and cut into chunks; each chunk is ONE contiguous, 16-byte
-// aligned blob -- header, values in jagged-diagonal (JDS) order, the chunk's row ids, its DISTINCT column ids,
-// JDS column offsets, row lengths and 16-bit chunk-local column indices -- moved to shared memory by one TMA
-// bulk copy.  Vectors keep the caller's numbering: rows and columns are reached through the two id lists.
 struct NmPackDesc { unsigned off16, bytes; };   // blob offset in 16-byte units, blob size in bytes
-struct NmPackHeader { int nr, nd, ne, maxlen_L; /* maxlen | L << 16 */ };
-struct NmPack {
-  DBuf<unsigned char> blob;
-  DBuf<NmPackDesc> desc;
-  DBuf<unsigned> slot_off8;               // per value slot: position of the double in the blob (8-byte units)
-  DBuf<int> slot_src;                     // per value slot: index into the matrix' value array
-  long long nslot = 0;
-  int nchunk = 0;                         // 0: not packed (fallback kernels)
-  int chunks_per_cta = 0, grid = 0;
-  int stage_bytes = 0, xs_doubles = 0, nstage = 0, smem_bytes = 0;
-  long long bytes = 0;                    // blob bytes = what one product streams from HBM
-  bool permuted = false;                  // vectors in pack order (see nm_pack_build_into)
-  DBuf<int> order;                        // permuted: pack position -> caller's index row
-};
-
-// Sliced JDS format read straight from global memory (k_sell, nm_spmv.cuh): the locality/length-class row order
-// of nm_pack.cu cut into slices of 256/(R*L) rows of one length class; inside a slice rows are sorted by length
-// and entry k of the j-th longest row sits at e0 + off[k] + j, so the lanes of a warp (neighbouring rows) read
-// neighbouring values / column ids (coalesced) with no padding.  One thread block per slice, L lanes per row.
-struct NmSellChunk { long long e0; int o0, r0, nr, L, maxlen, pad; };
-struct NmSell {
-  DBuf<double> val;                       // VPE values per entry, JDS order
-  DBuf<int> col;                          // (block-)column id per entry (in the vectors' numbering)
-  DBuf<int> off, rows, rowlen;            // JDS column offsets per slice; row ids; row lengths
-  DBuf<NmSellChunk> chunks;
-  DBuf<int> slot_src;                     // per value slot: index into the matrix' value array
-  long long nslot = 0;
-  int nchunk = 0;                         // 0: not built
-  long long bytes = 0;                    // bytes one product streams
-  bool permuted = false;                  // vectors in slice order
-  DBuf<int> order;                        // permuted: position -> caller's index row
-};
 
 // Warp-sliced ELL slabs in pack order (k_slab, nm_slab.cuh / nm_slab.cu): index rows grouped breadth-first into
 // compact chunks of at most T lanes (T = threads per CTA); a row of up to NM_SLAB_SPLIT entries is walked by ONE
@@ -239,8 +202,6 @@ struct NmParcsr {
   DBuf<int> bia, bja;
   DBuf<double> mval;
   NmHalo halo;
-  NmPack pack;
-  NmSell sell;
   long long values_version = 0;           // bumped whenever the values change (dependants refill their packs)
   double avg_row = 0.0;                   // mean entries per (block-)row processed by one subwarp
   long long fmt_bytes = 0;                // bytes one SpMV streams in the chosen format (matrix part)
@@ -256,9 +217,7 @@ struct NmChebIter {
   int deg = 0;
   std::vector<double> ak, bk;             // d_{k+1} = ak d_k + bk r_{k+1}
   DBuf<double> r, d0, d1;
-  // pack-order copy of M (nm_pack_build_into, permuted): the iteration runs on vectors kept in that order
-  NmPack ppack;
-  NmSell psell;
+  // pack-order slab copy of M (nm_slab_build_into): the iteration runs on vectors kept in that order
   NmSlab pslab;
   long long ppack_version = -1;
   DBuf<double> bp, xp;                    // b and x in pack order
@@ -342,22 +301,9 @@ bool nm_halo_ll_setup(NmHalo& h);            // collective: LL ghost slots in th
 void nm_halo_push_ll(NmParcsr& M, const double* x, const int* send_idx, const int* send_slot, unsigned tag, int buf);
 void nm_spmv(NmParcsr& M, const double* x, double* y);                 // y = M x   (device pointers)
 void nm_spmv_add(NmParcsr& M, const double* x, double* y);             // y += M x
-// packed format (nm_pack.cu): rp/idx = host row pointers and column ids of the chosen format, n (block-)rows
-void nm_pack_build(NmParcsr& M, const std::vector<int>& rp, const std::vector<int>& idx, int n);
-void nm_pack_build_into(NmParcsr& M, NmPack& P, const std::vector<int>& rp, const std::vector<int>& idx, int n,
-                        bool permuted);
-void nm_pack_fill(NmParcsr& M);                                        // (re)load the blob values from M.mval / M.a
-void nm_pack_fill_from(NmParcsr& M, NmPack& P);
-void nm_sell_build_into(NmParcsr& M, NmSell& S, const std::vector<int>& rp, const std::vector<int>& idx, int n,
-                        bool permuted);
-void nm_sell_fill_from(NmParcsr& M, NmSell& S);
-void nm_sell_clone(const NmParcsr& src, NmParcsr& dst);
 void nm_slab_build_into(NmParcsr& M, NmSlab& S, const std::vector<int>& rp, const std::vector<int>& idx, int n);
 void nm_slab_fill_from(NmParcsr& M, NmSlab& S);
-void nm_cm_order(int n, const std::vector<int>& rp, const std::vector<int>& idx, std::vector<int>& order);
 int nm_env_int(const char* name, int dflt);
-bool nm_use_sell();                                                    // NM_KERNEL_SELL (default 1): k_sell instead of k_pack
-void nm_pack_clone(const NmParcsr& src, NmParcsr& dst);                // same structure, values from dst
 // chebiter
 NmChebIter* nm_chebiter_build(double lb, double ub, int deg, NmParcsr* M);
 void nm_chebiter_solve(NmChebIter& C, const double* b, double* x);

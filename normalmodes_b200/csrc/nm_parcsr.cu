@@ -6,7 +6,7 @@
 #include <algorithm>
 
 // ---------------------------------------------------------------- halo (ghost-DOF) exchange
-__global__ void k_pack(double* __restrict__ buf, const double* __restrict__ x, const int* __restrict__ idx, int n) {
+__global__ void k_halo_gather(double* __restrict__ buf, const double* __restrict__ x, const int* __restrict__ idx, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) buf[i] = x[idx[i]];
 }
@@ -126,7 +126,7 @@ void nm_halo_exchange(NmParcsr& M, const double* x, const int* send_idx) {
     return;
   }
   if (h.nsend > 0) {
-    k_pack<<<nm_div_up(h.nsend, 256), 256, 0, c.stream>>>(h.sendbuf.p, x, send_idx ? send_idx : h.send_idx.p, h.nsend);
+    k_halo_gather<<<nm_div_up(h.nsend, 256), 256, 0, c.stream>>>(h.sendbuf.p, x, send_idx ? send_idx : h.send_idx.p, h.nsend);
     c.launches++;
   }
   NM_NCCL(ncclGroupStart());
@@ -360,23 +360,19 @@ static void choose_format(NmParcsr& M, const std::vector<int>& ia, const std::ve
   M.format = NM_FMT_CSR;
   M.avg_row = M.nrow ? (double)M.nnz / M.nrow : 0.0;
   M.fmt_bytes = 12ll * M.nnz + 4ll * (M.nrow + 1);
-  if (force && force[0] == '1') { nm_pack_build(M, ia, ja, M.nrow); return; }
+  if (force && force[0] == '1') return;
   if (aligned && M.nnz > 0 && detect_kron3(M.nrow, ia, ja, a, bia, bja, mval)) {
     M.format = NM_FMT_KRON3;
     M.nbrow = M.nrow / 3;
     M.bia.from_host(bia); M.bja.from_host(bja); M.mval.from_host(mval);
     M.avg_row = (double)bja.size() / M.nbrow;
     M.fmt_bytes = 12ll * (long long)bja.size() + 4ll * (M.nbrow + 1);
-    nm_pack_build(M, bia, bja, M.nbrow);
   } else if (aligned && M.nnz > 0 && detect_row3(M.nrow, ia, ja, bia, bja)) {
     M.format = NM_FMT_ROW3;
     M.nbrow = M.nrow / 3;
     M.bia.from_host(bia); M.bja.from_host(bja);
     M.avg_row = 3.0 * (double)bja.size() / M.nbrow;
     M.fmt_bytes = 8ll * M.nnz + 4ll * (long long)bja.size() + 4ll * (M.nbrow + 1);
-    nm_pack_build(M, bia, bja, M.nbrow);
-  } else {
-    nm_pack_build(M, ia, ja, M.nrow);
   }
 }
 
@@ -466,14 +462,6 @@ NmParcsr* nm_parcsr_scaled_copy(const NmParcsr& M, const double* dr, const doubl
                                                               S->halo.xg_cur);
     c.launches++;
   }
-  if (S->format == M.format) {
-    nm_pack_clone(M, *S);
-  } else {                                                    // KRON3 source -> CSR copy: pack the scalar rows
-    std::vector<int> hia(M.nrow + 1), hja((size_t)M.nnz);
-    M.ia.download(hia.data(), hia.size());
-    M.ja.download(hja.data(), hja.size());
-    nm_pack_build(*S, hia, hja, S->nrow);
-  }
   NM_CUDA(cudaStreamSynchronize(c.stream));
   return S.release();
 }
@@ -537,7 +525,6 @@ extern "C" int nm_parcsr_jacobi_scale(void* h, double sign, double* d_host) {
       k_kron_refresh<<<nm_div_up(M.nbrow, 128), 128, 0, c.stream>>>(M.nbrow, M.bia.p, M.ia.p, M.a.p, M.mval.p);
       c.launches++;
     }
-    nm_pack_fill(M);
   }
   if (d_host) d.download(d_host, n);
   NM_CUDA(cudaStreamSynchronize(c.stream));

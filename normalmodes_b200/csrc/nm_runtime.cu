@@ -174,6 +174,11 @@ static void p2p_setup() {
 // Allocation order is collective (every rank creates / frees the same matrices in the same order), and the offsets
 // are exchanged through the communicator afterwards, which also orders the zeroing before any peer's first store.
 static std::vector<std::pair<size_t, size_t>> g_win_free;       // (offset, bytes), 256-byte granules
+int nm_env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && v[0]) ? atoi(v) : dflt;
+}
+
 size_t nm_win_alloc(size_t bytes) {
   NmCtx& c = g_ctx;
   NM_REQUIRE(c.p2p, "nm_win_alloc without a peer window");

@@ -11,30 +11,14 @@
 //   KRON3  B = M (x) I3 (src/mod_cg_create_matrix.f90:1247-1259,1417-1434): scalar values and one
 //          block-column id per 3x3 block -> 12 bytes per 3 non-zeros of each of the 3 rows.
 //
-// The Chebyshev iterations (the hot loop) run on k_slabws / k_slab of nm_slab.cuh; the kernels in this file are the
-// general products (A, Ad, E, ET with the fused filter epilogue), the round-1a iteration kernels kept as fallbacks
-// and regression references (k_pack, k_sell), and the plain subwarp-per-row kernels.
-//
-// k_pack: HBM-bound streaming work, no tensor cores.  The matrix is stored once more in the
-// packed row-block format of nm_pack.cu: locality-ordered rows cut into chunks, each chunk one contiguous blob
-// (values in jagged-diagonal order, the chunk's row ids, its DISTINCT column ids, 16-bit chunk-local column
-// indices).  A persistent CTA walks a contiguous range of chunks; one elected thread moves each blob into
-// shared memory with a TMA bulk copy (cp.async.bulk + mbarrier complete_tx, L2 evict-first so the vectors stay
-// L2-resident) through an NSTAGE-deep ring, so the matrix stream never waits on the row structure.  The x
-// values a chunk needs are gathered from global memory ONCE per distinct column into shared memory (the L1
-// data pipe, one wavefront per cycle per SM, is what bounds a gather-per-entry SpMV on this part: ncu showed
-// 76% L1 throughput at 30% of HBM); the inner loop then runs entirely out of shared memory with conflict-free
-// JDS reads.  A scalar row is owned by L lanes (L chosen per chunk so rows x L fills the CTA); partial sums are
-// combined in a fixed order (deterministic) and the row's thread applies the fused epilogue with operands it
-// prefetched before the walk.
-//
-// Fallback kernels (k_spmv_*): one subwarp per (block-)row straight from global memory; used for
-// matrices whose rows do not fit a stage and for tiny matrices.
+// The Chebyshev iterations (the hot loop) run on k_slabws / k_slabpers / k_slab of nm_slab.cuh; the kernels in this
+// file are the general products (A, Ad, E, ET with the fused filter epilogue): one subwarp per (block-)row straight
+// from global memory, also the fallback of the iterations for matrices the slab packer refuses.  The mbarrier / TMA /
+// cp.async / flag-in-data helpers shared with nm_slab.cuh live here as well.
 #pragma once
 #include "nm_internal.h"
 
 #define NM_SPMV_THREADS 256
-#define NM_PACK_MAXDESC 256            // chunk descriptors a CTA keeps in shared memory
 
 template <int W>
 __device__ __forceinline__ double nm_subwarp_sum(double v) {
@@ -231,280 +215,12 @@ __device__ __forceinline__ uint64_t nm_policy_evict_first() {
   return p;
 }
 
-struct NmPackArgs {
-  const unsigned char* blob;
-  const NmPackDesc* desc;
-  int nchunk;
-  int chunks_per_cta;
-  const double* x;
-  const double* xg;
-  int ncol;
-  int stage_bytes, xs_doubles, nstage;
-  int dbg;                  // diagnostics (NM_PACK_DBG): 1 skip the x gather, 2 skip the JDS walk, 4 skip the epilogue
-};
-
 __device__ __forceinline__ void nm_cp_async8(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(nm_smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void nm_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// decoded view of a chunk blob sitting in shared memory
-struct NmPackView {
-  int nr, nd, ne, maxlen, L;
-  const double* sv;
-  const int* srows;
-  const int* scols;
-  const unsigned short* soff;
-  const unsigned short* slen;
-  const unsigned short* slidx;
-};
-template <int VPE>
-__device__ __forceinline__ NmPackView nm_pack_view(const unsigned char* st) {
-  const NmPackHeader h = *(const NmPackHeader*)st;
-  NmPackView v;
-  v.nr = h.nr; v.nd = h.nd; v.ne = h.ne; v.maxlen = h.maxlen_L & 0xffff; v.L = h.maxlen_L >> 16;
-  v.sv = (const double*)(st + 16);
-  v.srows = (const int*)(v.sv + (size_t)VPE * v.ne);
-  v.scols = v.srows + v.nr;
-  v.soff = (const unsigned short*)(((uintptr_t)(v.scols + v.nd) + 7) & ~(uintptr_t)7);
-  v.slen = v.soff + (v.maxlen + 1);
-  v.slidx = v.slen + v.nr;
-  return v;
-}
-
-// One persistent CTA = a contiguous range of chunks, software-pipelined so that ONE barrier per chunk remains:
-//   iteration it:  wait for blob it+1 (TMA, mbarrier ring) and start the asynchronous gather (cp.async, 8 bytes
-//                  per distinct column component) of the x values chunk it+1 needs into the other xs buffer;
-//                  load the epilogue operands of chunk it;
-//                  walk the JDS columns of chunk it out of shared memory (lane = index row x one of L lanes);
-//                  cp.async.wait_all + __syncthreads;  re-arm the freed stage with chunk it+NSTAGE;
-//                  fixed-order reduction of the L partial sums and fused epilogue, one thread per scalar row.
-template <int FMT, class Epi>
-__global__ void __launch_bounds__(NM_SPMV_THREADS, 3) k_pack(NmPackArgs A, Epi epi) {
-  constexpr int R = (FMT == NM_FMT_CSR) ? 1 : 3;          // scalar rows (and columns) per index entry
-  constexpr int VPE = (FMT == NM_FMT_ROW3) ? 9 : 1;
-  constexpr int PS = 3 * NM_SPMV_THREADS;                 // doubles per partial-sum buffer
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x;
-  const int c0 = blockIdx.x * A.chunks_per_cta;
-  const int nmine = min(A.chunks_per_cta, A.nchunk - c0);
-  if (nmine <= 0) return;
-  // shared layout: [descs][barriers][xs x2][partials x2][stages...]
-  NmPackDesc* sdesc = (NmPackDesc*)smem;
-  uint64_t* bars = (uint64_t*)(smem + NM_PACK_MAXDESC * sizeof(NmPackDesc));
-  double* xs0 = (double*)(bars + 8);
-  double* ps0 = xs0 + 2 * (size_t)A.xs_doubles;
-  unsigned char* stage0 = smem + ((NM_PACK_MAXDESC * sizeof(NmPackDesc) + 64 + 16 * (size_t)A.xs_doubles + 16 * PS + 15) &
-                                  ~(size_t)15);
-  if (tid < nmine) sdesc[tid] = A.desc[c0 + tid];
-  if (tid == 0) {
-    for (int s = 0; s < A.nstage; ++s) nm_mbar_init(bars + s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  uint64_t policy = 0;
-  auto issue = [&](int it) {
-    const NmPackDesc d = sdesc[it];
-    const int s = it % A.nstage;
-    nm_mbar_expect_tx(bars + s, d.bytes);
-    nm_bulk_g2s(stage0 + (size_t)s * A.stage_bytes, A.blob + 16ull * d.off16, d.bytes, bars + s, policy);
-  };
-  if (tid == 0) {
-    policy = nm_policy_evict_first();
-    for (int it = 0; it < min(A.nstage, nmine); ++it) issue(it);
-  }
-  const double* __restrict__ x = A.x;
-  const double* __restrict__ xg = A.xg;
-  const int ncol = A.ncol;
-  // wait for blob `it`, then start the asynchronous gather of its distinct x values
-  auto gather = [&](int it) {
-    const int s = it % A.nstage;
-    nm_mbar_wait(bars + s, (uint32_t)((it / A.nstage) & 1));
-    const NmPackView v = nm_pack_view<VPE>(stage0 + (size_t)s * A.stage_bytes);
-    double* xs = xs0 + (size_t)(it & 1) * A.xs_doubles;
-    if (A.dbg & 1) return;
-    for (int j = tid; j < R * v.nd; j += NM_SPMV_THREADS) {
-      const int node = j / R;
-      const int c = R * v.scols[node] + (j - R * node);
-      nm_cp_async8(xs + j, c < ncol ? x + c : xg + (c - ncol));
-    }
-  };
-  gather(0);
-  nm_cp_async_wait_all();
-  __syncthreads();
-  for (int it = 0; it < nmine; ++it) {
-    const NmPackView v = nm_pack_view<VPE>(stage0 + (size_t)(it % A.nstage) * A.stage_bytes);
-    const int nr = v.nr, L = v.L, S = R * nr;                    // S scalar rows (<= 256)
-    const double* xs = xs0 + (size_t)(it & 1) * A.xs_doubles;
-    double* ps = ps0 + (size_t)(it & 1) * PS;
-    if (it + 1 < nmine) gather(it + 1);
-    int row = 0;
-    typename Epi::In in;
-    if (tid < S && !(A.dbg & 4)) {
-      const int r = tid / R;
-      row = R * v.srows[r] + (tid - R * r);
-      in = epi.load(row);
-    }
-    // ---- JDS walk out of shared memory
-    if (FMT == NM_FMT_ROW3) {
-      // lane = (l, row r, column component c): 3 partial sums, one per scalar row of the node
-      if (tid < S * L && !(A.dbg & 2)) {
-        const int l = tid / S, slot = tid - l * S, r = slot / 3, c = slot - 3 * r;
-        const int len = v.slen[r];
-        const double* p0 = v.sv + c;
-        const double* p1 = p0 + 3 * (size_t)v.ne;
-        const double* p2 = p1 + 3 * (size_t)v.ne;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-#pragma unroll 2
-        for (int k = l; k < len; k += L) {
-          const int p = v.soff[k] + r;
-          const double xv = xs[3 * v.slidx[p] + c];
-          a0 += p0[3 * p] * xv;
-          a1 += p1[3 * p] * xv;
-          a2 += p2[3 * p] * xv;
-        }
-        // partial of scalar row 3r+i from column component c, lane l: ps[i][l][r][c]
-        ps[((0 * L + l) * nr + r) * 3 + c] = a0;
-        ps[((1 * L + l) * nr + r) * 3 + c] = a1;
-        ps[((2 * L + l) * nr + r) * 3 + c] = a2;
-      }
-    } else {
-      // lane = (l, index row r): R accumulators, x gathered once per entry for the R components
-      if (tid < nr * L && !(A.dbg & 2)) {
-        const int l = tid / nr, r = tid - l * nr;
-        const int len = v.slen[r];
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-#pragma unroll 2
-        for (int k = l; k < len; k += L) {
-          const int p = v.soff[k] + r;
-          const double m = v.sv[p];
-          const double* xp = xs + R * v.slidx[p];
-          a0 += m * xp[0];
-          if (R == 3) { a1 += m * xp[1]; a2 += m * xp[2]; }
-        }
-        double* q = ps + (size_t)(l * nr + r) * R;                // partials [l][r][component]
-        q[0] = a0;
-        if (R == 3) { q[1] = a1; q[2] = a2; }
-      }
-    }
-    nm_cp_async_wait_all();
-    __syncthreads();             // partials of chunk it visible; blob it consumed; xs of chunk it+1 complete
-    if (tid == 0 && it + A.nstage < nmine) issue(it + A.nstage);
-    if (tid < S && !(A.dbg & 4)) {
-      double acc = 0.0;
-      if (FMT == NM_FMT_ROW3) {
-        const int r = tid / 3, i = tid - 3 * r;
-        for (int l = 0; l < L; ++l) {
-          const double* q = ps + ((i * L + l) * nr + r) * 3;
-          acc += (q[0] + q[1]) + q[2];
-        }
-      } else {
-        for (int l = 0; l < L; ++l) acc += ps[l * S + tid];
-      }
-      epi.apply(row, acc, in);
-    }
-  }
-}
-
-// ================================================================ sliced-JDS kernel (no staging, no barriers)
-struct NmSellArgs {
-  const NmSellChunk* chunks;
-  const double* val;
-  const int* col;
-  const int* off;
-  const int* rows;
-  const int* rowlen;
-  const double* x;
-  const double* xg;
-  int ncol;
-};
-
-// One thread block per slice; thread = (scalar row of the slice, lane l of L).  Values and column ids are read
-// straight from global memory: in JDS order the lanes of a warp (neighbouring rows, same step) read neighbouring
-// words, so the matrix stream is coalesced without shared memory, the kernel runs at full occupancy and every lane
-// keeps 4 independent x gathers in flight.  L adjacent lanes share a long row (shuffle butterfly, fixed order).
-template <int FMT, class Epi>
-__global__ void __launch_bounds__(NM_SPMV_THREADS) k_sell(NmSellArgs A, Epi epi) {
-  constexpr int R = (FMT == NM_FMT_CSR) ? 1 : 3;
-  const NmSellChunk d = A.chunks[blockIdx.x];
-  const int L = d.L;
-  const int slot = threadIdx.x / L, l = threadIdx.x - slot * L;
-  const bool active = slot < R * d.nr;
-  const int r = active ? slot / R : 0, comp = slot - R * (slot / R);
-  const int len = active ? A.rowlen[d.r0 + r] : 0;
-  const int row = R * A.rows[d.r0 + r] + comp;
-  typename Epi::In in;
-  if (active && l == 0) in = epi.load(row);
-  const int* __restrict__ off = A.off + d.o0;
-  const int* __restrict__ col = A.col + d.e0;
-  const double* __restrict__ x = A.x;
-  const double* __restrict__ xg = A.xg;
-  const int ncol = A.ncol;
-  double acc = 0.0;
-  if (FMT == NM_FMT_ROW3) {
-    // scalar row 3r+comp: 3 consecutive values per block column at ((e0 + p)*9 + comp*3)
-    const double* __restrict__ val = A.val + 9 * d.e0 + 3 * comp;
-    double b0 = 0.0, b1 = 0.0;
-    int k = l;
-    for (; k + L < len; k += 2 * L) {
-      const int pa = off[k] + r, pb = off[k + L] + r;
-      const int ca = 3 * col[pa], cb = 3 * col[pb];
-      const double* va = val + 9 * (size_t)pa;
-      const double* vb = val + 9 * (size_t)pb;
-      const double xa0 = nm_ldx(x, xg, ncol, ca), xa1 = nm_ldx(x, xg, ncol, ca + 1), xa2 = nm_ldx(x, xg, ncol, ca + 2);
-      const double xb0 = nm_ldx(x, xg, ncol, cb), xb1 = nm_ldx(x, xg, ncol, cb + 1), xb2 = nm_ldx(x, xg, ncol, cb + 2);
-      b0 += va[0] * xa0; b0 += va[1] * xa1; b0 += va[2] * xa2;
-      b1 += vb[0] * xb0; b1 += vb[1] * xb1; b1 += vb[2] * xb2;
-    }
-    if (k < len) {
-      const int pa = off[k] + r;
-      const int ca = 3 * col[pa];
-      const double* va = val + 9 * (size_t)pa;
-      b0 += va[0] * nm_ldx(x, xg, ncol, ca); b0 += va[1] * nm_ldx(x, xg, ncol, ca + 1); b0 += va[2] * nm_ldx(x, xg, ncol, ca + 2);
-    }
-    acc = b0 + b1;
-  } else {
-    const double* __restrict__ val = A.val + d.e0;
-    double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
-    int k = l;
-    for (; k + 3 * L < len; k += 4 * L) {
-      const int p0 = off[k] + r, p1 = off[k + L] + r, p2 = off[k + 2 * L] + r, p3 = off[k + 3 * L] + r;
-      int c0 = col[p0], c1 = col[p1], c2 = col[p2], c3 = col[p3];
-      if (FMT == NM_FMT_KRON3) { c0 = 3 * c0 + comp; c1 = 3 * c1 + comp; c2 = 3 * c2 + comp; c3 = 3 * c3 + comp; }
-      const double v0 = val[p0], v1 = val[p1], v2 = val[p2], v3 = val[p3];
-      const double x0 = nm_ldx(x, xg, ncol, c0), x1 = nm_ldx(x, xg, ncol, c1), x2 = nm_ldx(x, xg, ncol, c2),
-                   x3 = nm_ldx(x, xg, ncol, c3);
-      b0 += v0 * x0; b1 += v1 * x1; b2 += v2 * x2; b3 += v3 * x3;
-    }
-    for (; k < len; k += L) {
-      const int p0 = off[k] + r;
-      int c0 = col[p0];
-      if (FMT == NM_FMT_KRON3) c0 = 3 * c0 + comp;
-      b0 += val[p0] * nm_ldx(x, xg, ncol, c0);
-    }
-    acc = (b0 + b1) + (b2 + b3);
-  }
-  for (int o = L >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (active && l == 0) epi.apply(row, acc, in);
-}
-
-template <int FMT, class Epi>
-static inline void nm_sell_launch(NmParcsr& M, NmSell& S, const double* x, const Epi& epi) {
-  NmCtx& c = nm_ctx();
-  NmSellArgs A;
-  A.chunks = S.chunks.p; A.val = S.val.p; A.col = S.col.p; A.off = S.off.p; A.rows = S.rows.p; A.rowlen = S.rowlen.p;
-  A.x = x; A.xg = M.halo.xg_cur ? M.halo.xg_cur : x; A.ncol = M.ncol;
-  k_sell<FMT, Epi><<<S.nchunk, NM_SPMV_THREADS, 0, c.stream>>>(A, epi);
-  c.launches++;
-}
-template <class Epi>
-static inline void nm_sell_dispatch(NmParcsr& M, NmSell& S, const double* x, const Epi& epi) {
-  if (M.format == NM_FMT_KRON3) nm_sell_launch<NM_FMT_KRON3, Epi>(M, S, x, epi);
-  else if (M.format == NM_FMT_ROW3) nm_sell_launch<NM_FMT_ROW3, Epi>(M, S, x, epi);
-  else nm_sell_launch<NM_FMT_CSR, Epi>(M, S, x, epi);
-}
-
-// ---------------------------------------------------------------- fallback kernels (global-memory subwarp per row)
+// ---------------------------------------------------------------- product kernels (global-memory subwarp per row)
 template <int W, class Epi>
 __global__ void __launch_bounds__(NM_SPMV_THREADS)
 k_spmv_csr(int nrow, int ncol, const int* __restrict__ ia, const int* __restrict__ ja, const double* __restrict__ a,
@@ -599,49 +315,10 @@ static inline void nm_spmv_launch_w(NmParcsr& M, const double* x, const Epi& epi
   c.launches++;
 }
 
-template <int FMT, class Epi>
-static inline void nm_pack_launch(NmParcsr& M, NmPack& P, const double* x, const Epi& epi) {
-  NmCtx& c = nm_ctx();
-  NmPackArgs A;
-  A.blob = P.blob.p; A.desc = P.desc.p; A.nchunk = P.nchunk; A.chunks_per_cta = P.chunks_per_cta;
-  A.x = x; A.xg = M.halo.xg_cur ? M.halo.xg_cur : x; A.ncol = M.ncol;
-  A.stage_bytes = P.stage_bytes; A.xs_doubles = P.xs_doubles; A.nstage = P.nstage;
-  static const int dbg = getenv("NM_PACK_DBG") ? atoi(getenv("NM_PACK_DBG")) : 0;
-  A.dbg = dbg;
-  static bool attr_set = false;                                  // per template instantiation
-  if (!attr_set) {
-    NM_CUDA(cudaFuncSetAttribute(k_pack<FMT, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
-  k_pack<FMT, Epi><<<P.grid, NM_SPMV_THREADS, P.smem_bytes, c.stream>>>(A, epi);
-  c.launches++;
-}
-
-// Product through an explicit pack (NmChebIter's pack-order copy): x and the epilogue vectors are in P's order.
-template <class Epi>
-static inline void nm_spmv_sell_epi(NmParcsr& M, NmSell& S, const double* x, const Epi& epi, const int* send_idx) {
-  nm_halo_exchange(M, x, send_idx);
-  nm_sell_dispatch(M, S, x, epi);
-}
-template <class Epi>
-static inline void nm_spmv_pack_epi(NmParcsr& M, NmPack& P, const double* x, const Epi& epi, const int* send_idx) {
-  nm_halo_exchange(M, x, send_idx);
-  if (M.format == NM_FMT_KRON3) nm_pack_launch<NM_FMT_KRON3, Epi>(M, P, x, epi);
-  else if (M.format == NM_FMT_ROW3) nm_pack_launch<NM_FMT_ROW3, Epi>(M, P, x, epi);
-  else nm_pack_launch<NM_FMT_CSR, Epi>(M, P, x, epi);
-}
-
 // Halo exchange (if any) + SpMV with the given epilogue.  x: device, owned part only.
 template <class Epi>
 static inline void nm_spmv_epi(NmParcsr& M, const double* x, const Epi& epi) {
   nm_halo_exchange(M, x);
-  if (M.sell.nchunk > 0) { nm_sell_dispatch(M, M.sell, x, epi); return; }
-  if (M.pack.nchunk > 0) {
-    if (M.format == NM_FMT_KRON3) nm_pack_launch<NM_FMT_KRON3, Epi>(M, M.pack, x, epi);
-    else if (M.format == NM_FMT_ROW3) nm_pack_launch<NM_FMT_ROW3, Epi>(M, M.pack, x, epi);
-    else nm_pack_launch<NM_FMT_CSR, Epi>(M, M.pack, x, epi);
-    return;
-  }
   const double r = M.avg_row;              // entries one subwarp walks through
   if (r <= 6.0) nm_spmv_launch_w<4, Epi>(M, x, epi);
   else if (r <= 12.0) nm_spmv_launch_w<8, Epi>(M, x, epi);

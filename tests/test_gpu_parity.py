@@ -425,63 +425,6 @@ def test_error_paths(nm):
         mv.chebiter_setup(-1.0, 2.0, 5, h)
 
 
-@pytest.mark.parametrize("sell,entries,distinct,maxgrid,stages", [(1, 0, 0, 0, 2), (1, 4, 0, 0, 2), (1, 1000, 0, 0, 2),
-                                                                  (0, 0, 0, 0, 2), (0, 256, 64, 2, 2),
-                                                                  (0, 512, 4096, 3, 1), (0, 96, 40, 1, 4)])
-def test_packed_kernel_ring_and_chunking(nm, monkeypatch, sell, entries, distinct, maxgrid, stages):
-    """TMA-staged packed row-block kernel (k_pack) against the oracle product for the three formats, with chunk
-    sizes / grid limits that force many chunks per CTA (ring wrap-around, mbarrier phase flips, L = 1..32 lanes per
-    row) and against the global-memory fallback kernels; fused ChebIter epilogue included."""
-    from oracle import fem, solver
-    from normalmodes_b200 import matvec as mv
-    monkeypatch.setenv("NM_NATURAL_PACK", "1")             # packs are only built inside NmChebIter by default
-    monkeypatch.setenv("NM_KERNEL_SELL", str(sell))        # 1: sliced-JDS kernel (k_sell, entries = NM_SELL_TARGET)
-    if sell and entries:
-        monkeypatch.setenv("NM_SELL_TARGET", str(entries))
-    if entries:
-        monkeypatch.setenv("NM_PACK_ENTRIES", str(entries))
-        monkeypatch.setenv("NM_PACK_DISTINCT", str(distinct))
-    monkeypatch.setenv("NM_PACK_STAGES", str(stages))
-    if maxgrid:
-        monkeypatch.setenv("NM_PACK_MAXGRID", str(maxgrid))
-    rng = np.random.default_rng(99)
-    for name in ("prem3k_p1_j2", "const3k_p2_j1"):
-        c = load_case(name)
-        for k, m in to_coomat(c["mats"]).items():
-            S = fem.to_scipy(c["mats"][k])
-            x = rng.uniform(-1, 1, S.shape[1])
-            monkeypatch.setenv("NM_NO_PACK", "0"); monkeypatch.setenv("NM_NO_SELL", "0")
-            h = mv.parcsr_create(m)
-            y = mv.parcsr_matvec(h, x, S.shape[0])
-            nm.nm_parcsr_free(h)
-            assert (np.abs(y - S @ x) <= _spmv_tol(S, x)).all(), (name, k)
-            monkeypatch.setenv("NM_NO_PACK", "1"); monkeypatch.setenv("NM_NO_SELL", "1")
-            h = mv.parcsr_create(m)
-            y2 = mv.parcsr_matvec(h, x, S.shape[0])
-            nm.nm_parcsr_free(h)
-            assert (np.abs(y - y2) <= 2 * _spmv_tol(S, x)).all(), (name, k)
-    # fused Chebyshev step through the packed kernel (KRON3 B~)
-    monkeypatch.setenv("NM_NO_PACK", "0"); monkeypatch.setenv("NM_NO_SELL", "0")
-    c = load_case("const3k_p2_j1")
-    m = to_coomat(c["mats"])["B"]
-    h = mv.parcsr_create(m)
-    from normalmodes_b200._lib import check, dptr
-    d = np.empty(m.Gsiz)
-    check(nm.nm_parcsr_jacobi_scale(h, C.c_double(1.0), dptr(d)))
-    assert mv.parcsr_info(h)["format"] == "KRON3"
-    ref, _ = fem.jacobi_scale(c["mats"]["B"], 1.0)
-    St = fem.to_scipy(ref)
-    lb, ub = 0.2, 4.5
-    for deg in (1, 2, 7):
-        cheb = mv.chebiter_setup(lb, ub, deg, h)
-        b = rng.standard_normal(St.shape[0])
-        xg = mv.chebiter_solve(cheb, b)
-        xr = solver.chebiter(St, lb, ub, deg, b)
-        assert np.abs(xg - xr).max() <= 1e-13 * np.abs(xr).max()
-        nm.nm_chebiter_free(cheb)
-    nm.nm_parcsr_free(h)
-
-
 SLAB_CONFIGS = [dict(), dict(NM_SLAB_PERS="1"), dict(NM_SLAB_PERS="1", NM_SLAB_FLOW="0"), dict(NM_SLAB_PERS="1", NM_SLAB_PERS_STAGES="2"),
                 dict(NM_SLAB_PERS="1", NM_SLAB_PERS_STAGES="3", NM_SLAB_MAXGRID="5"),
                 dict(NM_SLAB_PERS="1", NM_SLAB_FLOW="0", NM_SLAB_PERS_STAGES="3", NM_SLAB_MAXGRID="5"),
@@ -497,8 +440,7 @@ SLAB_CONFIGS = [dict(), dict(NM_SLAB_PERS="1"), dict(NM_SLAB_PERS="1", NM_SLAB_F
                 dict(NM_SLAB_ENTRIES="200", NM_SLAB_DISTINCT="140", NM_SLAB_MAXGRID="2", NM_SLAB_WS="0"),
                 dict(NM_SLAB_THREADS="64", NM_SLAB_ENTRIES="96", NM_SLAB_DISTINCT="140", NM_SLAB_MAXGRID="1", NM_SLAB_STAGES="2", NM_SLAB_XS="2"),
                 dict(NM_SLAB_THREADS="64", NM_SLAB_ENTRIES="96", NM_SLAB_DISTINCT="140", NM_SLAB_MAXGRID="1", NM_SLAB_STAGES="5", NM_SLAB_XS="4"),
-                dict(NM_SLAB_SPLIT="4", NM_SLAB_MAXGRID="3", NM_SLAB_STAGES="4", NM_SLAB_WS="0"), dict(NM_CHEB_KERNEL="pack"),
-                dict(NM_CHEB_KERNEL="sell")]
+                dict(NM_SLAB_SPLIT="4", NM_SLAB_MAXGRID="3", NM_SLAB_STAGES="4", NM_SLAB_WS="0"), dict(NM_CHEB_KERNEL="plain")]
 
 
 @pytest.mark.parametrize("cfg", SLAB_CONFIGS)
@@ -507,14 +449,15 @@ def test_chebiter_slab_kernel_configs(nm, monkeypatch, cfg):
     warp-specialised producers with full/empty mbarriers) and the whole iteration through the persistent kernel k_slabpers
     (pinned + ring stages, grid barrier or per-chunk dataflow flags) on the
     KRON3 B~ (P1 and P2) and the CSR Ap~, with chunk sizes / grid limits that force many chunks per CTA (ring
-    wrap-around, mbarrier phase flips), against the oracle's Chebyshev iteration; k_pack / k_sell stay covered."""
+    wrap-around, mbarrier phase flips), against the oracle's Chebyshev iteration; the plain subwarp kernels (the fallback of
+    matrices the packer refuses) stay covered."""
     from oracle import fem, solver
     from normalmodes_b200 import matvec as mv
     from normalmodes_b200._lib import check, dptr
     for k, v in cfg.items():
         monkeypatch.setenv(k, v)
-    want = dict(pack=1, sell=2).get(cfg.get("NM_CHEB_KERNEL", "slab"),
-                                    3 if cfg.get("NM_SLAB_WS") == "0" else (5 if cfg.get("NM_SLAB_PERS") == "1" else 4))
+    want = 0 if cfg.get("NM_CHEB_KERNEL") == "plain" else (
+        3 if cfg.get("NM_SLAB_WS") == "0" else (5 if cfg.get("NM_SLAB_PERS") == "1" else 4))
     for name, key, sign in (("const3k_p2_j1", "B", 1.0), ("prem3k_p1_j2", "B", 1.0), ("prem3k_p2_j2", "Ap", -1.0)):
         c = load_case(name)
         m = to_coomat(c["mats"])[key]

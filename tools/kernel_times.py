@@ -28,7 +28,7 @@ def main():
     p.add_argument("--reps", type=int, default=20)
     p.add_argument("--ncu-range", action="store_true",
                    help="only run [cudaProfilerStart; one Ap~ solve; one B~ solve; cudaProfilerStop] after warm-up (for "
-                        "ncu --profile-from-start off --kernel-name-base demangled -k regex:k_pack --launch-skip/-c)")
+                        "ncu --profile-from-start off --kernel-name-base demangled -k regex:k_slabws --launch-skip/-c)")
     a = p.parse_args()
     import torch
     torch.cuda.set_device(0)

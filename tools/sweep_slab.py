@@ -1,5 +1,5 @@
 """Tuning sweep of the fused ChebIter step kernels on the bench workload's B~ (KRON3) and Ap~ (CSR): k_slab
-configurations (threads, stages, split, caps) against k_pack / k_sell.  Diagnostic only, not a bench value.
+configurations (threads, stages, split, caps, persistent variant).  Diagnostic only, not a bench value.
     python tools/sweep_slab.py [--ntet N] [--which B,Ap] [--out gpurun_out/sweep_slab.json]"""
 import argparse
 import ctypes as C
@@ -13,21 +13,21 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 KEYS = ("NM_CHEB_KERNEL", "NM_SLAB_THREADS", "NM_SLAB_STAGES", "NM_SLAB_SPLIT", "NM_SLAB_ENTRIES", "NM_SLAB_DISTINCT",
-        "NM_SLAB_CTAS_PER_SM", "NM_PACK_BANK_AWARE", "NM_PACK_ORDER", "NM_SLAB_WS", "NM_SLAB_PRODUCERS", "NM_SLAB_XS", "NM_SLAB_PDL")
+        "NM_SLAB_CTAS_PER_SM", "NM_PACK_BANK_AWARE", "NM_PACK_ORDER", "NM_SLAB_WS", "NM_SLAB_PRODUCERS", "NM_SLAB_XS", "NM_SLAB_PDL",
+        "NM_SLAB_PERS", "NM_SLAB_FLOW")
 
 CONFIGS = [
-    dict(NM_SLAB_WS="0"),
     dict(),
-    dict(NM_SLAB_PDL="0"),
+    dict(NM_SLAB_SPLIT="16"),
+    dict(NM_SLAB_SPLIT="8"),
     dict(NM_SLAB_PRODUCERS="2"),
     dict(NM_SLAB_PRODUCERS="6"),
-    dict(NM_SLAB_STAGES="3", NM_SLAB_XS="3"),
-    dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="8"),
-    dict(NM_SLAB_THREADS="256", NM_SLAB_SPLIT="16"),
-    dict(NM_SLAB_THREADS="256", NM_SLAB_SPLIT="12"),
-    dict(NM_SLAB_THREADS="256", NM_SLAB_SPLIT="20", NM_SLAB_ENTRIES="4096", NM_SLAB_DISTINCT="720"),
-    dict(NM_SLAB_THREADS="128", NM_SLAB_SPLIT="16", NM_SLAB_ENTRIES="1792", NM_SLAB_DISTINCT="380"),
-    dict(NM_SLAB_THREADS="128", NM_SLAB_SPLIT="16", NM_SLAB_ENTRIES="1792", NM_SLAB_DISTINCT="380", NM_SLAB_STAGES="3", NM_SLAB_XS="3"),
+    dict(NM_SLAB_XS="3"),
+    dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="12"),
+    dict(NM_SLAB_ENTRIES="2560", NM_SLAB_DISTINCT="480", NM_SLAB_STAGES="3", NM_SLAB_XS="3"),
+    dict(NM_SLAB_THREADS="128", NM_SLAB_SPLIT="12", NM_SLAB_ENTRIES="1792", NM_SLAB_DISTINCT="380"),
+    dict(NM_PACK_BANK_AWARE="1"),
+    dict(NM_SLAB_PERS="1", NM_SLAB_FLOW="0"),
 ]
 
 
@@ -63,7 +63,7 @@ def main():
                 os.environ.pop(k, None)
             os.environ.update(cfg)
             t0 = time.time()
-            deg = 20
+            deg = 12
             cheb = mvmod.chebiter_setup(0.25, 4.35, deg, h)
             tb = time.time() - t0
             kind = C.c_int(); nb = C.c_longlong()
@@ -72,7 +72,7 @@ def main():
             for _ in range(2):
                 fn()
             torch.cuda.synchronize()
-            reps = 10
+            reps = 4
             e0.record(stream)
             for _ in range(reps):
                 fn()
