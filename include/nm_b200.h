@@ -65,7 +65,8 @@ int nm_chebiter_solve_dev(void* cheb, const double* b_dev, double* x_dev);
 int nm_chebiter_stats(void* cheb, long long* nsolve, long long* nmatvec, int* deg, double* lmin, double* lmax);
 /* kind: 0 plain subwarp kernels (fallback), 1-2 retired, 3 warp-sliced ELL slabs (k_slab), 4 the same with
    producer/consumer warps (k_slabws, one launch per step), 5 the whole iteration in one persistent cooperative launch
-   (k_slabpers, default: grid barrier per step, in-kernel flag-in-data halo on several GPUs);
+   (k_slabpers, NM_SLAB_PERS=1: grid barrier or per-chunk flags between steps); on several GPUs kinds 4 and 5 exchange the
+   halo inside the kernel through flag-in-data slots;
    bytes: matrix bytes one step streams */
 int nm_chebiter_pack_info(void* cheb, int* kind, long long* bytes);
 /* diagnostic (NM_SLAB_TRACE=1): per CTA and chunk 8 clock64 stamps of the last k_slab launch, [grid][64][8] */

@@ -381,7 +381,7 @@ extern "C" int nm_chebiter_solve_dev(void* h, const double* b_dev, double* x_dev
 }
 // kind: 0 = plain kernels on the caller's numbering (1, 2: the retired round-1a kernels),
 // 3 = TMA-staged warp-sliced ELL slabs (k_slab), 4 = the same, warp-specialised (k_slabws), 5 = the whole iteration in one
-// persistent cooperative launch (k_slabpers, default); all on vectors kept in pack order; bytes = matrix bytes one iteration step streams
+// persistent cooperative launch (k_slabpers, NM_SLAB_PERS=1); all on vectors kept in pack order; bytes = matrix bytes one iteration step streams
 extern "C" int nm_chebiter_pack_info(void* h, int* kind, long long* bytes) {
   NM_API_BEGIN
   NmChebIter& C = *(NmChebIter*)h;

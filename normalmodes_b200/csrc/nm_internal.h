@@ -223,7 +223,7 @@ struct NmChebIter {
   DBuf<double> bp, xp;                    // b and x in pack order
   DBuf<int> send_idx_p;                   // halo send list in pack order
   // per pack-order index row the peer stores of its new direction: in-kernel halo of the persistent kernel
-  // (k_slabpers, default) and of the per-step fused kernel (NM_HALO_FUSED=1)
+  // (k_slabpers, NM_SLAB_PERS=1) and of the per-step fused kernel (default on several GPUs)
   bool fused = false;
   bool pers = false;                      // whole iteration in ONE cooperative launch (grid barrier between steps)
   bool pers_multi_ok = false;             // the halo pattern allows the in-kernel exchange (symmetric)

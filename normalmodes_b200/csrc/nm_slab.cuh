@@ -13,11 +13,13 @@
 // walk directly.  The matrix is streamed by TMA bulk copies (cp.async.bulk + mbarrier complete_tx, L2 evict-first so
 // the vectors stay L2-resident) through a stage ring; the x values of the chunks AHEAD are gathered once per distinct
 // column with cp.async.
-//   k_slab    one __syncthreads per chunk (all warps gather, then walk);
-//   k_slabws  (default) warp-specialised: producer warps keep the rings full, consumer warps only walk; stages and x
-//             buffers are handed over with full/empty mbarriers; consecutive steps are chained by programmatic
-//             dependent launch; on several GPUs the producers poll the peers' arrival flags before the chunks that
-//             have ghost columns (nm_parcsr.cu: k_halo_push).
+//   k_slab     one __syncthreads per chunk (all warps gather, then walk; NM_SLAB_WS=0);
+//   k_slabws   (default) warp-specialised: producer warps keep the rings full, consumer warps only walk; stages and x
+//              buffers are handed over with full/empty mbarriers; consecutive steps are chained by programmatic
+//              dependent launch; on several GPUs (FUSED) the epilogue stores the boundary rows into the peers'
+//              flag-in-data slots and the producers poll the slots of the ghost columns they gather;
+//   k_slabpers (NM_SLAB_PERS=1) the whole iteration in one cooperative launch: pinned + ring stages, a grid barrier or
+//              per-chunk dependency flags between steps, the same in-kernel halo.
 #pragma once
 #include "nm_spmv.cuh"
 
@@ -481,10 +483,14 @@ __global__ void __launch_bounds__(32 * (NC + 8)) k_slabws(NmSlabWsArgs W, Epi ep
 }
 
 // ---------------------------------------------------------------- persistent variant: the WHOLE iteration in one launch
-// "one persistent kernel per solve".  The per-step launches of k_slabws cost ~5 us of drain + launch +
-// first-gather latency per step even with dependent launch (an Ap~ step on the bench workload is 9 us whatever the
-// tile shape, profiles/r1d_sweep_slab.json), and on several GPUs every step adds two system-scope fences and a flag
-// flight.  k_slabpers is launched cooperatively ONCE per solve: every CTA keeps its chunk range for all deg steps;
+// "one persistent kernel per solve" (opt-in, NM_SLAB_PERS=1).  Motivation: the per-step launches of
+// k_slabws cost ~5 us of drain + launch + first-gather latency per step even with dependent launch (an Ap~ step on the
+// 200k-tet workload is 9 us whatever the tile shape, profiles/r1d_sweep_slab.json).  Measured outcome (one B200,
+// profiles/r2b_kernel_times_pers_barrier.json, gpurun_out/r2c_*): the software grid barrier costs MORE than the
+// hardware's grid completion + dependent launch -- B~ step 32.8 us against 28.4, Ap~ 10.4 against 8.7 -- and the
+// dataflow variant more still (42.4 / 17.5: one poll + fence + named barrier per chunk visit serialises the
+// producers); on 2 GPUs the barrier variant is ~5% ahead of the per-step kernels (profiles/r2l_*).  Kept, tested, not
+// the default.  k_slabpers is launched cooperatively ONCE per solve: every CTA keeps its chunk range for all deg steps;
 //   * matrix: the first P chunks of a CTA stay pinned in their stages (all of them when the range fits the ring: the
 //     slab is then read from HBM once per SOLVE); the others stream through 2 ring stages, the copies of step k+1
 //     running ahead across the step boundary (the matrix is read-only);
