@@ -19,14 +19,14 @@ KEYS = ("NM_CHEB_KERNEL", "NM_SLAB_THREADS", "NM_SLAB_STAGES", "NM_SLAB_SPLIT", 
 CONFIGS = [
     dict(),
     dict(NM_SLAB_SPLIT="16"),
-    dict(NM_SLAB_SPLIT="8"),
-    dict(NM_SLAB_PRODUCERS="2"),
     dict(NM_SLAB_PRODUCERS="6"),
     dict(NM_SLAB_XS="3"),
-    dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="12"),
     dict(NM_SLAB_ENTRIES="2560", NM_SLAB_DISTINCT="480", NM_SLAB_STAGES="3", NM_SLAB_XS="3"),
-    dict(NM_SLAB_THREADS="128", NM_SLAB_SPLIT="12", NM_SLAB_ENTRIES="1792", NM_SLAB_DISTINCT="380"),
+    dict(NM_SLAB_THREADS="512", NM_SLAB_SPLIT="12"),
     dict(NM_PACK_BANK_AWARE="1"),
+    dict(NM_SLAB_SPLIT="8"),
+    dict(NM_SLAB_PRODUCERS="2"),
+    dict(NM_SLAB_THREADS="128", NM_SLAB_SPLIT="12", NM_SLAB_ENTRIES="1792", NM_SLAB_DISTINCT="380"),
     dict(NM_SLAB_PERS="1", NM_SLAB_FLOW="0"),
 ]
 
