@@ -376,6 +376,76 @@ def test_f90_abi_with_host_callbacks(nm):
     nm.pevsl_finish_f90_(C.byref(pAB))
 
 
+def test_f90_abi_device_resident_operators_fluid_solid(nm):
+    """INTEGRATION.md level 1, the intended drop-in: mod_matvec.f90 / mod_pevsl.f90's call order through the by-reference
+    `*_f90_` symbols, with the operators registered as device-resident objects (NM_SETBMV_PARCSR_F90 /
+    NM_SETAMV_FLUIDSOLID_F90 instead of the host callbacks) on the fluid-solid PREM3k demo with gravity: the whole
+    filtered Lanczos stays on the GPU; eigenvalues against the independent truth."""
+    from oracle import fem, solver
+    c = load_case("prem3k_p1_j2")
+    mats = c["mats"]
+    Bs, d = fem.jacobi_scale(mats["B"])                         # Bdiagscaling stays on the host (src/mod_matvec.f90:252-342)
+    Aps, dp = fem.jacobi_scale(mats["Ap"], sign=-1.0)            # Ap := -CGM%Ap, Apdiagscaling (:137, 345-441)
+    n, npr = c["num"]["N"], c["num"]["Np"]
+    i4 = lambda v: C.byref(C.c_int32(v))
+    f8 = lambda v: C.byref(C.c_double(v))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    dp_ = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    comm = C.c_int32(0)
+    keep = []
+
+    def create(m, nr, nc):
+        h = C.c_uint64(0)
+        rs = np.array([0, nr], dtype=np.int32); cs = np.array([0, nc], dtype=np.int32)
+        ia = m["ia"].astype(np.int32); ja = m["ja"].astype(np.int32); a = np.ascontiguousarray(m["a"], dtype=np.float64)
+        keep.extend([rs, cs, ia, ja, a])
+        nm.pevsl_parcsrcreate_f90_(i4(nr), i4(nc), ip(rs), ip(cs), ip(ia), ip(ja), dp_(a), C.byref(comm), C.byref(h))
+        return h
+
+    def bounds_and_cheb(h, size, mlan, lanstep, deg):
+        p = C.c_uint64(0)
+        nm.pevsl_start_f90_(C.byref(comm), C.byref(p))
+        nm.pevsl_setprobsizes_f90_(C.byref(p), i4(size), i4(size), i4(-1))
+        nm.nm_setamv_parcsr_f90_(C.byref(p), C.byref(h))
+        lmin, lmax = C.c_double(), C.c_double()
+        nm.pevsl_lanbounds_f90_(C.byref(p), i4(mlan), i4(lanstep), f8(1e-12), C.byref(lmin), C.byref(lmax))
+        cheb = C.c_uint64(0)
+        nm.pevsl_setup_chebiter_f90_(C.byref(lmin), C.byref(lmax), i4(deg), C.byref(h), C.byref(cheb))
+        nm.pevsl_finish_f90_(C.byref(p))
+        return cheb
+    sBV = create(Bs, n, n)
+    chebB = bounds_and_cheb(sBV, n, 1000, 2000, 25)                # src/mod_matvec.f90:75-95
+    sAdV = create(mats["Ad"], n, n)
+    sApV = create(Aps, npr, npr)
+    chebAp = bounds_and_cheb(sApV, npr, 2000, 3000, 25)            # :152-174
+    sEV = create(mats["E"], n, npr); sETV = create(mats["ET"], npr, n)
+    pAB = C.c_uint64(0)                                             # src/mod_pevsl.f90:54-84
+    nm.pevsl_start_f90_(C.byref(comm), C.byref(pAB))
+    nm.pevsl_setprobsizes_f90_(C.byref(pAB), i4(n), i4(n), i4(-1))
+    nm.nm_setbmv_parcsr_f90_(C.byref(pAB), C.byref(sBV))
+    nm.pevsl_setbsol_chebiter_f90_(C.byref(pAB), i4(2), C.byref(chebB))
+    dd = np.ascontiguousarray(d, dtype=np.float64); ddp = np.ascontiguousarray(dp, dtype=np.float64)
+    nm.nm_setamv_fluidsolid_f90_(C.byref(pAB), C.byref(sAdV), C.byref(sEV), C.byref(sETV), C.byref(chebAp), dp_(dd), dp_(ddp))
+    nm.pevsl_set_geneig_f90_(C.byref(pAB))
+    lmin, lmax = C.c_double(), C.c_double()
+    nm.pevsl_lanbounds_f90_(C.byref(pAB), i4(3000), i4(5000), f8(1e-5), C.byref(lmin), C.byref(lmax))
+    g = c["g"]
+    a_, b_ = solver.freq_interval(g["lowfreq"], g["upfreq"], lmin.value)
+    xintv = np.array([a_, b_, lmin.value, lmax.value])
+    pol = C.c_uint64(0)
+    nm.pevsl_findpol_f90_(dp_(xintv), f8(0.8), f8(0.7), C.byref(pol))
+    nm.pevsl_cheblannr_f90_(C.byref(pAB), dp_(xintv), i4(9624), f8(1e-5), C.byref(pol))
+    nev = C.c_int32(0)
+    nm.pevsl_get_nev_f90_(C.byref(pAB), C.byref(nev))
+    truth = np.array(g["truth_eigs"]); truth = truth[(truth >= a_) & (truth <= b_)]
+    assert nev.value == len(truth) == 61
+    vals = np.empty(nev.value); vecs = np.empty(nev.value * n)
+    nm.pevsl_copy_result_f90_(C.byref(pAB), dp_(vals), dp_(vecs), i4(n))
+    assert np.max(np.abs(np.sort(vals) - truth) / truth) < 1e-10
+    nm.pevsl_freepol_f90_(C.byref(pol))
+    nm.pevsl_finish_f90_(C.byref(pAB))
+
+
 def test_lanbounds_bounded_basis_and_breakdown(nm, monkeypatch):
     """LanTrbounds replacement (src/mod_matvec.f90:85,162): (a) with the basis capped far below the step count the
     explicit restart still returns tight OUTER bounds; (b) an exact breakdown (3 distinct eigenvalues: the Krylov
