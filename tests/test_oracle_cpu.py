@@ -190,3 +190,37 @@ def test_c_port_matches_numpy_oracle(name):
     ref = solver.chebav(pol, v, ops)
     got = co.chebav(pol["deg"], pol["mu"], pol["cc"], pol["dd"], v)
     assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+def test_truth_eigenvalues_against_survey_probe_and_physics(golden):
+    """Pins that do not come from the oracle's own code:
+    (a) the survey session's throw-away probe of CONST3k -- standard P1 elasticity + consistent mass with dense LAPACK,
+        written independently of oracle/fem.py -- found 271 eigenvalues in the demo band, the lowest at 0.37418, 0.37422,
+        0.37459, 0.37515, 0.37527 mHz (0T2), then 0.39331 ... 0.39400 (0S2), 0.51220, and lambda_max(B^-1 A) = 2.89537e-3;
+    (b) the analytic 0T2 of a homogeneous ball, (l-1) j_l(x) = x j_{l+1}(x) => x = 2.501, f = x vs / (2 pi a) = 0.361 mHz,
+        multiplicity 2l+1 = 5 (3 k elements: percent-level discretisation error);
+    (c) multiplet structure 2l+1 of the spherical demo models (splitting by the unstructured mesh stays at the 1e-3 level)."""
+    g = golden["const3k_p1_j1"]
+    f = np.sqrt(np.array(g["truth_eigs"])) / (2 * np.pi) * 1e3
+    assert len(f) == 271
+    assert np.allclose(f[:5], [0.37418, 0.37422, 0.37459, 0.37515, 0.37527], atol=6e-6)
+    assert np.allclose(f[5:11], [0.39331, 0.39344, 0.39357, 0.39373, 0.39400, 0.51220], atol=6e-6)
+    assert abs(g["oracle_lanczos"]["bounds"][1] - 2.89537e-3) < 1e-8
+    f0t2 = 2.501 * 5.7735 / (2 * np.pi * 6371.0) * 1e3
+    assert abs(f[:5].mean() / f0t2 - 1.0) < 0.05 and f[5] - f[4] > 10 * (f[4] - f[0])
+
+    def multiplets(fr, rel=4e-3):
+        out = [1]
+        for a, b in zip(fr[:-1], fr[1:]):
+            if (b - a) < rel * b:
+                out[-1] += 1
+            else:
+                out.append(1)
+        return out
+    fm = np.sqrt(np.array(golden["mtopo100k_p1_j1"]["truth_eigs"])) / (2 * np.pi) * 1e3
+    assert multiplets(fm) == [5, 5, 3, 7]                      # Moon model: l = 2, 2, 1, 3
+    fp = np.sqrt(np.array(golden["prem3k_p2_j2"]["truth_eigs"])) / (2 * np.pi) * 1e3
+    assert multiplets(fp) == [3, 5, 5, 3]                      # PREM, P2, gravity: a triplet (l = 1), two quintuplets, a triplet
+    fc = np.sqrt(np.array(golden["const3k_p2_j1"]["truth_eigs"])) / (2 * np.pi) * 1e3
+    assert multiplets(fc)[:3] == [5, 5, 3]
+    assert abs(fc[:5].mean() / f0t2 - 1.0) < 0.012            # P2 on the same mesh: 0T2 within 1.2 % of the analytic value
