@@ -92,3 +92,35 @@ def test_bench_stacks_rank_blocks_into_global_csr():
     x = rng.standard_normal(n)
     y = ops.apply_A(x)
     assert np.abs(y - S @ x).max() <= 1e-13 * np.abs(y).max()
+
+
+def test_bench_workload_partition_host_side():
+    """bench.py's multi-rank workload construction without a GPU: P2 node count without a topology probe, RCB parts of
+    equal size, and per-rank row blocks that tile the global problem for 2, 3 and 8 ranks."""
+    import bench
+    from normalmodes_b200 import meshgen, partition
+    from normalmodes_b200.create_matrix import Fem
+    mesh = meshgen.build_mesh(2500, seed=1)
+    model = meshgen.build_model(mesh, 2)
+    f1 = Fem(mesh, model["vs"], 2, nproc=1)
+    N1, Np1 = f1.N, f1.Np
+    f1.free()
+    for nranks in (2, 3, 8):
+        nn = bench.p2_node_count(mesh)
+        f0 = Fem(mesh, model["vs"], 2, nproc=nranks, part=np.zeros(nn, dtype=np.int32), rank=0)
+        assert f0.nn == nn
+        X = partition.node_coordinates(mesh, f0)
+        f0.free()
+        part = partition.rcb(X, nranks)
+        cnt = np.bincount(part, minlength=nranks)
+        assert cnt.max() - cnt.min() <= nranks                  # recursive bisection: one node of slack per level
+        rows = 0; prows = 0
+        for r in range(nranks):
+            f = Fem(mesh, model["vs"], 2, nproc=nranks, part=part, rank=r)
+            assert (f.N, f.Np) == (N1, Np1)                    # the global sizes do not depend on the partition
+            B = f.matrix("B", values=False)
+            Ap = f.matrix("Ap", values=False)
+            rows += B.siz(r); prows += Ap.siz(r)
+            assert B.col.min() >= 0 and B.col.max() < N1
+            f.free()
+        assert rows == N1 and prows == Np1
